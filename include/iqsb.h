@@ -1,0 +1,193 @@
+/*
+ * iqsb.h -- C ABI of libiqs_b200.so: the B200 (sm_100a) state-vector engine that sits
+ * under the Intel-QS `iqs::QubitRegister<Type>` class.
+ *
+ * Nothing like this exists in the reference: its seam is a set of C++ function
+ * templates (Loop_SN/Loop_DN/Loop_TN/ScaleState, reference include/highperfkernels.hpp:10-34)
+ * plus loops written inline in the QubitRegister methods.  Each entry point below names
+ * the reference interface it replaces (file:line are relative to the reference tree).
+ *
+ * Conventions
+ *  - every function returns 0 on success and a negative code on failure; the message of
+ *    the last failure of the calling thread is available from iqsb_last_error().
+ *  - amplitudes are interleaved (re, im); a register shard holds `local_amps` amplitudes of
+ *    `double` (IQSB_F64, ComplexDP) or `float` (IQSB_F32, ComplexSP).
+ *  - 2x2 matrices are passed as `const double m[8]`, row-major, (re, im) per entry:
+ *    m = {m00.re, m00.im, m01.re, m01.im, m10.re, m10.im, m11.re, m11.im}.
+ *    For IQSB_F32 registers the entries are rounded to float once, on the host.
+ *  - `pos` arguments are *positions* (data-qubit indices, reference qureg.hpp:80-85) and
+ *    are local: pos < log2(local_amps), unless the function name says `_global`.
+ *  - all work is enqueued on the context's stream; functions returning a scalar, and
+ *    iqsb_download / iqsb_sync, synchronise that stream.
+ *  - there is no CPU fallback: without a CUDA device iqsb_init fails.
+ */
+#ifndef IQSB_H
+#define IQSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct iqsb_ctx iqsb_ctx;     /* one per process: device, stream, NCCL communicator */
+typedef struct iqsb_state iqsb_state; /* one register shard (+ optional tmp area)            */
+
+enum { IQSB_F64 = 0, IQSB_F32 = 1 };
+enum {
+  IQSB_MEM_DEVICE = 0, /* cudaMalloc: fastest, IPC-exportable (needed for nranks > 1)  */
+  IQSB_MEM_MANAGED = 1 /* cudaMallocManaged, device-preferred: host pointer is valid   */
+};
+enum { IQSB_OK = 0, IQSB_ERR_CUDA = -1, IQSB_ERR_NCCL = -2, IQSB_ERR_ARG = -3, IQSB_ERR_STATE = -4 };
+enum { IQSB_SUM = 0, IQSB_MAX = 1 };
+#define IQSB_UNIQUE_ID_BYTES 128
+
+/* ---- library ------------------------------------------------------------------------ */
+int iqsb_version(void);
+const char *iqsb_last_error(void);
+
+/* ---- context: replaces iqs::mpi::Environment Init/Finalize/rank queries
+ *      (include/mpi_env.hpp:46-145, src/mpi_env.cpp:95-230) ----------------------------- */
+/* rank 0 creates the NCCL id; the launcher hands the 128 bytes to the other ranks. */
+int iqsb_unique_id(void *out_128_bytes);
+/* device < 0 means "rank % visible devices". uid may be NULL when nranks == 1. */
+int iqsb_init(int rank, int nranks, const void *uid, int device, iqsb_ctx **out);
+int iqsb_finalize(iqsb_ctx *ctx);
+int iqsb_rank(const iqsb_ctx *ctx);
+int iqsb_nranks(const iqsb_ctx *ctx);
+int iqsb_device(const iqsb_ctx *ctx);
+int iqsb_sync(iqsb_ctx *ctx);
+/* adopt an external cudaStream_t (e.g. torch's current stream) so that the caller's
+ * CUDA events bracket our launches; NULL restores the context's own stream. */
+int iqsb_set_stream(iqsb_ctx *ctx, void *cuda_stream);
+void *iqsb_get_stream(iqsb_ctx *ctx);
+/* number of kernels this context launched since creation (bench.py: gpu_launches). */
+uint64_t iqsb_launch_count(const iqsb_ctx *ctx);
+/* device-side timing on the context's stream (CUDA events). */
+int iqsb_timer_start(iqsb_ctx *ctx);
+int iqsb_timer_stop(iqsb_ctx *ctx, double *elapsed_ms);
+
+/* ---- scalar collectives: replace MPI_Allreduce_x / MPI_Bcast_x / MPI_Barrier
+ *      (include/mpi_utils.hpp:34-78, src/mpi_env.cpp:499-509) ------------------------- */
+int iqsb_allreduce_f64(iqsb_ctx *ctx, double *inout, int n, int op);
+int iqsb_bcast_f64(iqsb_ctx *ctx, double *inout, int n, int root);
+int iqsb_barrier(iqsb_ctx *ctx);
+
+/* ---- memory: replaces QubitRegister::Allocate/Resize/dtor
+ *      (src/qureg_init.cpp:44-75,148-187,449-457) ------------------------------------- */
+int iqsb_alloc(iqsb_ctx *ctx, uint64_t local_amps, uint64_t tmp_amps, int dtype, int mem_kind,
+               iqsb_state **out);
+int iqsb_free(iqsb_state *st);
+uint64_t iqsb_local_amps(const iqsb_state *st);
+int iqsb_dtype(const iqsb_state *st);
+void *iqsb_device_ptr(iqsb_state *st);
+/* host-dereferenceable pointer to the shard (IQSB_MEM_MANAGED only, else NULL). */
+void *iqsb_host_ptr(iqsb_state *st);
+/* make the shard resident in HBM again after host accesses (managed memory only; no-op else). */
+int iqsb_prefetch_device(iqsb_state *st);
+int iqsb_upload(iqsb_state *st, const void *host_amps, uint64_t first_amp, uint64_t count);
+int iqsb_download(iqsb_state *st, void *host_amps, uint64_t first_amp, uint64_t count);
+/* dst[i] = src[i] (copy constructor, src/qureg_init.cpp:364-379). */
+int iqsb_copy(iqsb_state *dst, const iqsb_state *src);
+
+/* ---- initialisation: Initialize("base"/"++++") and friends
+ *      (src/qureg_init.cpp:218-347; qureg_utils.cpp:173-184) -------------------------- */
+int iqsb_fill_const(iqsb_state *st, double re, double im); /* InitializationWithSameAmplitudeEverywhere */
+int iqsb_set_amp(iqsb_state *st, uint64_t local_index, double re, double im); /* SetGlobalAmplitude on the owner */
+int iqsb_get_amp(iqsb_state *st, uint64_t local_index, double *re, double *im);
+/* state[i] = U[-1,1) + i U[-1,1) from a counter-based generator (splitmix64 of seed and the
+ * global amplitude index) -- benchmark/test input only, not the reference's mt19937 stream. */
+int iqsb_fill_random(iqsb_state *st, uint64_t seed, uint64_t global_offset);
+
+/* ---- gate kernels -------------------------------------------------------------------- */
+/* 1-qubit gate on local position pos over the index range [sind, eind):
+ * replaces Loop_DN(sind, eind, pos, state, state, 0, 1<<pos, m, ...)
+ * (src/highperfkernels.cpp:287-380; called from qureg_apply1qubitgate.cpp:206). */
+int iqsb_gate1(iqsb_state *st, unsigned pos, const double m[8], uint64_t sind, uint64_t eind);
+/* controlled 1-qubit gate, both positions local: replaces the two Loop_TN calls of
+ * ApplyControlled1QubitGate_helper (src/qureg_applyctrl1qubitgate.cpp:312-345,
+ * src/highperfkernels.cpp:397-486). */
+int iqsb_cgate1(iqsb_state *st, unsigned cpos, unsigned tpos, const double m[8], uint64_t sind,
+                uint64_t eind);
+/* swap-family gate: 2x2 `m` on the {pos1=1,pos2=0} <-> {pos1=0,pos2=1} subspace with
+ * pos1 < pos2 both local: replaces Loop_TN in ApplySwap_helper (src/qureg_applyswap.cpp:203-206). */
+int iqsb_swap2x2(iqsb_state *st, unsigned pos1, unsigned pos2, const double m[8]);
+/* two-qubit diagonal gate, amp *= d[2*bit(pos1)+bit(pos2)] (src/qureg_applydiag.cpp:157-224).
+ * A position >= log2(local_amps) is "global": its bit is taken from glb_start. */
+int iqsb_diag2(iqsb_state *st, unsigned pos1, unsigned pos2, const double d[8], uint64_t glb_start);
+/* state[i] *= s for i in [start, end): ScaleState (src/highperfkernels.cpp:501-520). */
+int iqsb_scale(iqsb_state *st, const double s[2], uint64_t start, uint64_t end);
+/* amp *= s for the amplitudes whose bit `pos` is 1 (diagonal 1-qubit gate diag(1, s) and, with
+ * cpos >= 0, its controlled form); used for diag(d0,d1) gates as scale-by-bit. */
+int iqsb_phase_by_bit(iqsb_state *st, int cpos, unsigned pos, const double d0[2], const double d1[2]);
+/* general 4x4 gate on local positions (high, low): Apply2QubitGate (src/qureg_apply2qubitgate.cpp:15-73);
+ * m is 16 complex numbers row-major, basis index t = 2*bit(pos_high) + bit(pos_low). */
+int iqsb_gate2(iqsb_state *st, unsigned pos_high, unsigned pos_low, const double m[32]);
+
+/* ---- gate fusion: replaces ApplyFusedGates (src/qureg_fusion.cpp:55-94) -------------- */
+typedef struct iqsb_fgate {
+  int32_t kind; /* 0 = 1-qubit gate on `target`; 1 = controlled gate (control, target) */
+  int32_t control;
+  int32_t target; /* target position, must be < the tile exponent */
+  int32_t pad;
+  double m[8];
+} iqsb_fgate;
+/* apply `ngates` gates in order in ONE sweep over HBM; every target must be < max tile
+ * exponent (iqsb_fused_max_log2tile()), controls may be any local position. */
+int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates);
+int iqsb_fused_max_log2tile(const iqsb_state *st);
+
+/* ---- reductions (warp-shuffle + fixed-order second stage; deterministic run to run) -- */
+/* sum |a|^2 over local amplitudes with bit pos == 1: GetProbability (src/qureg_measure.cpp:150-167) */
+int iqsb_prob1(iqsb_state *st, unsigned pos, double *out);
+/* sum_i (-1)^popcount((glb_start+i) & mask) |a_i|^2: ExpectationValue (src/qureg_expectval.cpp:173-185) */
+int iqsb_parity_expect(iqsb_state *st, uint64_t mask, uint64_t glb_start, double *out);
+/* sum |a|^2: ComputeNorm before sqrt (src/qureg_utils.cpp:236-255) */
+int iqsb_norm2(iqsb_state *st, double *out);
+/* sum conj(b_i) a_i: ComputeOverlap (src/qureg_utils.cpp:259-300); out = {re, im} */
+int iqsb_overlap(iqsb_state *a, iqsb_state *b, double out[2]);
+/* max_i |a_i - s b_i|: MaxAbsDiff (src/qureg_utils.cpp:35-72) */
+int iqsb_maxabsdiff(iqsb_state *a, iqsb_state *b, const double s[2], double *out);
+/* sum_i |a_i - b_i|^2: MaxL2NormDiff (src/qureg_utils.cpp:127-158) */
+int iqsb_l2diff(iqsb_state *a, iqsb_state *b, double *out);
+/* out[0] = any |a_i|^2 > tol with bit pos == 0, out[1] = same with bit pos == 1:
+ * IsClassicalBit / GetClassicalValue (src/qureg_measure.cpp:19-81,183-262). pos >= log2(local)
+ * is global: every amplitude counts for the bit value found in glb_start. */
+int iqsb_any_above(iqsb_state *st, unsigned pos, double tol, uint64_t glb_start, int out[2]);
+/* 1 if the two shards hold equal values (operator==, src/qureg_utils.cpp:17-31) */
+int iqsb_equal(iqsb_state *a, iqsb_state *b, int *out);
+/* -sum p ln p and the Google moments (src/qureg_utils.cpp:305-450): out[0] = sum -p ln p,
+ * out[1] = sum -ln p, out[2..10] = sum p^k, k = 2..10 (local, unscaled). */
+int iqsb_entropy_stats(iqsb_state *st, double out[11]);
+
+/* ---- measurement / element-wise ------------------------------------------------------ */
+/* zero the amplitudes whose bit pos != value: CollapseQubit (src/qureg_measure.cpp:92-126) */
+int iqsb_collapse(iqsb_state *st, unsigned pos, int value);
+/* a[i] += f * b[i]: AmplitudeWiseSum (src/qureg_utils.cpp:199-226) */
+int iqsb_axpy(iqsb_state *a, const iqsb_state *b, const double f[2]);
+
+/* ---- qubit reordering: PermuteLocalQubits (src/qureg_permute.cpp:55-104) ------------- */
+/* new[j] = old[i] where bit b of i becomes bit dst_bit[b] of j, b < log2(local_amps). */
+int iqsb_permute_local(iqsb_state *st, const uint8_t *dst_bit, unsigned nbits);
+
+/* ---- distributed (nranks > 1): fused compute + NVLink peer access -------------------- */
+/* publish the shard to the peers (cudaIpc) -- collective over all ranks of the context. */
+int iqsb_share(iqsb_state *st);
+/* 1-qubit gate on global position pos >= M: replaces HP_Distrpair(P) (src/qureg_apply1qubitgate.cpp:18-169) */
+int iqsb_gate1_global(iqsb_state *st, unsigned M, unsigned pos, const double m[8]);
+/* controlled gate, control local (cpos < M), target global: replaces HP_Distrpair(C,T)
+ * (src/qureg_applyctrl1qubitgate.cpp:24-220) */
+int iqsb_cgate1_global(iqsb_state *st, unsigned M, unsigned cpos, unsigned tpos, const double m[8]);
+/* swap-family gate with pos1 < pos2, pos2 >= M: replaces HP_DistrSwap (src/qureg_applyswap.cpp:247-480) */
+int iqsb_swap2x2_global(iqsb_state *st, unsigned M, unsigned pos1, unsigned pos2, const double m[8]);
+/* whole-shard move: this rank's shard goes to `dst_rank`, it receives `src_rank`'s:
+ * replaces the Sendrecv loop of PermuteGlobalQubits (src/qureg_permute.cpp:174-185) */
+int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank);
+/* bytes this context moved over NVLink (peer loads + peer stores) since creation. */
+uint64_t iqsb_nvlink_bytes(const iqsb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IQSB_H */

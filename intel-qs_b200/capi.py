@@ -1,0 +1,344 @@
+"""ctypes binding of the C ABI in include/iqsb.h (libiqs_b200.so).
+
+This is plumbing for the Python harness (tests, bench.py); it adds no behaviour of its own.
+There is no fallback: if the CUDA library is missing, ``load()`` raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libiqs_b200.so")
+
+F64, F32 = 0, 1
+MEM_DEVICE, MEM_MANAGED = 0, 1
+SUM, MAX = 0, 1
+
+_lib = None
+
+c_u64, c_uint, c_int, c_dbl, c_vp = ctypes.c_uint64, ctypes.c_uint, ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+
+
+class IqsbError(RuntimeError):
+    pass
+
+
+class FGate(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("control", ctypes.c_int32), ("target", ctypes.c_int32), ("pad", ctypes.c_int32), ("m", c_dbl * 8)]
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise IqsbError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    L.iqsb_last_error.restype = ctypes.c_char_p
+    L.iqsb_launch_count.restype = c_u64
+    L.iqsb_nvlink_bytes.restype = c_u64
+    L.iqsb_local_amps.restype = c_u64
+    L.iqsb_device_ptr.restype = c_vp
+    L.iqsb_host_ptr.restype = c_vp
+    L.iqsb_get_stream.restype = c_vp
+    sig = {
+        "iqsb_unique_id": [c_vp],
+        "iqsb_init": [c_int, c_int, c_vp, c_int, ctypes.POINTER(c_vp)],
+        "iqsb_finalize": [c_vp],
+        "iqsb_rank": [c_vp], "iqsb_nranks": [c_vp], "iqsb_device": [c_vp],
+        "iqsb_sync": [c_vp],
+        "iqsb_set_stream": [c_vp, c_vp], "iqsb_get_stream": [c_vp],
+        "iqsb_launch_count": [c_vp], "iqsb_nvlink_bytes": [c_vp],
+        "iqsb_timer_start": [c_vp], "iqsb_timer_stop": [c_vp, ctypes.POINTER(c_dbl)],
+        "iqsb_allreduce_f64": [c_vp, c_vp, c_int, c_int],
+        "iqsb_bcast_f64": [c_vp, c_vp, c_int, c_int],
+        "iqsb_barrier": [c_vp],
+        "iqsb_alloc": [c_vp, c_u64, c_u64, c_int, c_int, ctypes.POINTER(c_vp)],
+        "iqsb_free": [c_vp],
+        "iqsb_local_amps": [c_vp], "iqsb_dtype": [c_vp], "iqsb_device_ptr": [c_vp], "iqsb_host_ptr": [c_vp],
+        "iqsb_prefetch_device": [c_vp],
+        "iqsb_upload": [c_vp, c_vp, c_u64, c_u64],
+        "iqsb_download": [c_vp, c_vp, c_u64, c_u64],
+        "iqsb_copy": [c_vp, c_vp],
+        "iqsb_fill_const": [c_vp, c_dbl, c_dbl],
+        "iqsb_set_amp": [c_vp, c_u64, c_dbl, c_dbl],
+        "iqsb_get_amp": [c_vp, c_u64, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)],
+        "iqsb_fill_random": [c_vp, c_u64, c_u64],
+        "iqsb_gate1": [c_vp, c_uint, c_vp, c_u64, c_u64],
+        "iqsb_cgate1": [c_vp, c_uint, c_uint, c_vp, c_u64, c_u64],
+        "iqsb_swap2x2": [c_vp, c_uint, c_uint, c_vp],
+        "iqsb_diag2": [c_vp, c_uint, c_uint, c_vp, c_u64],
+        "iqsb_scale": [c_vp, c_vp, c_u64, c_u64],
+        "iqsb_phase_by_bit": [c_vp, c_int, c_uint, c_vp, c_vp],
+        "iqsb_gate2": [c_vp, c_uint, c_uint, c_vp],
+        "iqsb_fused": [c_vp, c_vp, c_int],
+        "iqsb_fused_max_log2tile": [c_vp],
+        "iqsb_prob1": [c_vp, c_uint, ctypes.POINTER(c_dbl)],
+        "iqsb_parity_expect": [c_vp, c_u64, c_u64, ctypes.POINTER(c_dbl)],
+        "iqsb_norm2": [c_vp, ctypes.POINTER(c_dbl)],
+        "iqsb_overlap": [c_vp, c_vp, c_vp],
+        "iqsb_maxabsdiff": [c_vp, c_vp, c_vp, ctypes.POINTER(c_dbl)],
+        "iqsb_l2diff": [c_vp, c_vp, ctypes.POINTER(c_dbl)],
+        "iqsb_any_above": [c_vp, c_uint, c_dbl, c_u64, c_vp],
+        "iqsb_equal": [c_vp, c_vp, ctypes.POINTER(c_int)],
+        "iqsb_entropy_stats": [c_vp, c_vp],
+        "iqsb_collapse": [c_vp, c_uint, c_int],
+        "iqsb_axpy": [c_vp, c_vp, c_vp],
+        "iqsb_permute_local": [c_vp, c_vp, c_uint],
+        "iqsb_share": [c_vp],
+        "iqsb_gate1_global": [c_vp, c_uint, c_uint, c_vp],
+        "iqsb_cgate1_global": [c_vp, c_uint, c_uint, c_uint, c_vp],
+        "iqsb_swap2x2_global": [c_vp, c_uint, c_uint, c_uint, c_vp],
+        "iqsb_permute_global": [c_vp, c_int, c_int],
+    }
+    for name, args in sig.items():
+        getattr(L, name).argtypes = args
+    _lib = L
+    return L
+
+
+DECLARED_SYMBOLS = None  # filled lazily from include/iqsb.h by tests
+
+
+def _chk(rc):
+    if rc != 0:
+        raise IqsbError(f"[{rc}] {load().iqsb_last_error().decode(errors='replace')}")
+
+
+def _m(m, n=8):
+    m = np.asarray(m)
+    if m.dtype.kind == "c":
+        m = np.ascontiguousarray(m, dtype=np.complex128).ravel().view(np.float64)
+    m = np.ascontiguousarray(m, dtype=np.float64).ravel()
+    assert m.size == n, (m.size, n)
+    return m
+
+
+def _c2(z):
+    z = complex(z)
+    return np.array([z.real, z.imag], dtype=np.float64)
+
+
+def unique_id():
+    buf = ctypes.create_string_buffer(128)
+    _chk(load().iqsb_unique_id(buf))
+    return buf.raw
+
+
+class Context:
+    def __init__(self, rank=0, nranks=1, uid=None, device=-1):
+        self.L = load()
+        h = c_vp()
+        ub = ctypes.create_string_buffer(uid, 128) if uid is not None else None
+        _chk(self.L.iqsb_init(rank, nranks, ub, device, ctypes.byref(h)))
+        self.h = h
+        self.rank, self.nranks = rank, nranks
+
+    def close(self):
+        if self.h:
+            self.L.iqsb_finalize(self.h)
+            self.h = None
+
+    def sync(self):
+        _chk(self.L.iqsb_sync(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        _chk(self.L.iqsb_set_stream(self.h, c_vp(cuda_stream_ptr)))
+
+    def launches(self):
+        return int(self.L.iqsb_launch_count(self.h))
+
+    def nvlink_bytes(self):
+        return int(self.L.iqsb_nvlink_bytes(self.h))
+
+    def timer_start(self):
+        _chk(self.L.iqsb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = c_dbl()
+        _chk(self.L.iqsb_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def allreduce(self, values, op=SUM):
+        v = np.ascontiguousarray(values, dtype=np.float64).copy()
+        _chk(self.L.iqsb_allreduce_f64(self.h, v.ctypes.data_as(c_vp), v.size, op))
+        return v
+
+    def bcast(self, values, root=0):
+        v = np.ascontiguousarray(values, dtype=np.float64).copy()
+        _chk(self.L.iqsb_bcast_f64(self.h, v.ctypes.data_as(c_vp), v.size, root))
+        return v
+
+    def barrier(self):
+        _chk(self.L.iqsb_barrier(self.h))
+
+    def alloc(self, local_amps, tmp_amps=0, dtype=F64, mem=MEM_DEVICE):
+        return State(self, local_amps, tmp_amps, dtype, mem)
+
+
+class State:
+    """One register shard in HBM.  Method names follow include/iqsb.h."""
+
+    def __init__(self, ctx, local_amps, tmp_amps=0, dtype=F64, mem=MEM_DEVICE):
+        self.ctx, self.L = ctx, ctx.L
+        h = c_vp()
+        _chk(self.L.iqsb_alloc(ctx.h, local_amps, tmp_amps, dtype, mem, ctypes.byref(h)))
+        self.h = h
+        self.local_amps = int(local_amps)
+        self.dtype = dtype
+        self.np_dtype = np.complex128 if dtype == F64 else np.complex64
+
+    def free(self):
+        if self.h:
+            self.L.iqsb_free(self.h)
+            self.h = None
+
+    # memory
+    def upload(self, host, first=0):
+        a = np.ascontiguousarray(host, dtype=self.np_dtype)
+        _chk(self.L.iqsb_upload(self.h, a.ctypes.data_as(c_vp), first, a.size))
+
+    def download(self, first=0, count=None):
+        count = self.local_amps - first if count is None else count
+        out = np.empty(count, dtype=self.np_dtype)
+        _chk(self.L.iqsb_download(self.h, out.ctypes.data_as(c_vp), first, count))
+        return out
+
+    def copy_from(self, other):
+        _chk(self.L.iqsb_copy(self.h, other.h))
+
+    def fill_const(self, z):
+        z = complex(z)
+        _chk(self.L.iqsb_fill_const(self.h, z.real, z.imag))
+
+    def fill_random(self, seed, global_offset=0):
+        _chk(self.L.iqsb_fill_random(self.h, seed, global_offset))
+
+    def set_amp(self, i, z):
+        z = complex(z)
+        _chk(self.L.iqsb_set_amp(self.h, i, z.real, z.imag))
+
+    def get_amp(self, i):
+        re, im = c_dbl(), c_dbl()
+        _chk(self.L.iqsb_get_amp(self.h, i, ctypes.byref(re), ctypes.byref(im)))
+        return complex(re.value, im.value)
+
+    # gates
+    def gate1(self, pos, m, sind=0, eind=None):
+        mm = _m(m)
+        _chk(self.L.iqsb_gate1(self.h, pos, mm.ctypes.data_as(c_vp), sind, self.local_amps if eind is None else eind))
+
+    def cgate1(self, cpos, tpos, m, sind=0, eind=None):
+        mm = _m(m)
+        _chk(self.L.iqsb_cgate1(self.h, cpos, tpos, mm.ctypes.data_as(c_vp), sind, self.local_amps if eind is None else eind))
+
+    def swap2x2(self, pos1, pos2, m):
+        mm = _m(m)
+        _chk(self.L.iqsb_swap2x2(self.h, pos1, pos2, mm.ctypes.data_as(c_vp)))
+
+    def diag2(self, pos1, pos2, d, glb_start=0):
+        dd = _m(d)
+        _chk(self.L.iqsb_diag2(self.h, pos1, pos2, dd.ctypes.data_as(c_vp), glb_start))
+
+    def scale(self, f, start=0, end=None):
+        ff = _c2(f)
+        _chk(self.L.iqsb_scale(self.h, ff.ctypes.data_as(c_vp), start, self.local_amps if end is None else end))
+
+    def phase_by_bit(self, cpos, pos, d0, d1):
+        a, b = _c2(d0), _c2(d1)
+        _chk(self.L.iqsb_phase_by_bit(self.h, cpos, pos, a.ctypes.data_as(c_vp), b.ctypes.data_as(c_vp)))
+
+    def gate2(self, pos_high, pos_low, m16):
+        mm = np.ascontiguousarray(np.asarray(m16, dtype=np.complex128).reshape(16)).view(np.float64)
+        _chk(self.L.iqsb_gate2(self.h, pos_high, pos_low, mm.ctypes.data_as(c_vp)))
+
+    def fused(self, gates):
+        """gates: list of (kind, control, target, m8)."""
+        arr = (FGate * len(gates))()
+        for i, (kind, c, t, m) in enumerate(gates):
+            arr[i].kind, arr[i].control, arr[i].target = kind, c, t
+            mm = _m(m)
+            for k in range(8):
+                arr[i].m[k] = mm[k]
+        _chk(self.L.iqsb_fused(self.h, arr, len(gates)))
+
+    def fused_max_log2tile(self):
+        return int(self.L.iqsb_fused_max_log2tile(self.h))
+
+    # reductions
+    def prob1(self, pos):
+        o = c_dbl()
+        _chk(self.L.iqsb_prob1(self.h, pos, ctypes.byref(o)))
+        return o.value
+
+    def parity_expect(self, mask, glb_start=0):
+        o = c_dbl()
+        _chk(self.L.iqsb_parity_expect(self.h, mask, glb_start, ctypes.byref(o)))
+        return o.value
+
+    def norm2(self):
+        o = c_dbl()
+        _chk(self.L.iqsb_norm2(self.h, ctypes.byref(o)))
+        return o.value
+
+    def overlap(self, other):
+        o = np.zeros(2)
+        _chk(self.L.iqsb_overlap(self.h, other.h, o.ctypes.data_as(c_vp)))
+        return complex(o[0], o[1])
+
+    def maxabsdiff(self, other, f=1.0):
+        o = c_dbl()
+        ff = _c2(f)
+        _chk(self.L.iqsb_maxabsdiff(self.h, other.h, ff.ctypes.data_as(c_vp), ctypes.byref(o)))
+        return o.value
+
+    def l2diff(self, other):
+        o = c_dbl()
+        _chk(self.L.iqsb_l2diff(self.h, other.h, ctypes.byref(o)))
+        return o.value
+
+    def any_above(self, pos, tol, glb_start=0):
+        o = (c_int * 2)()
+        _chk(self.L.iqsb_any_above(self.h, pos, tol, glb_start, o))
+        return int(o[0]), int(o[1])
+
+    def equal(self, other):
+        o = c_int()
+        _chk(self.L.iqsb_equal(self.h, other.h, ctypes.byref(o)))
+        return bool(o.value)
+
+    def entropy_stats(self):
+        o = np.zeros(11)
+        _chk(self.L.iqsb_entropy_stats(self.h, o.ctypes.data_as(c_vp)))
+        return o
+
+    def collapse(self, pos, value):
+        _chk(self.L.iqsb_collapse(self.h, pos, int(bool(value))))
+
+    def axpy(self, other, f=1.0):
+        ff = _c2(f)
+        _chk(self.L.iqsb_axpy(self.h, other.h, ff.ctypes.data_as(c_vp)))
+
+    def permute_local(self, dst_bit):
+        a = np.ascontiguousarray(dst_bit, dtype=np.uint8)
+        _chk(self.L.iqsb_permute_local(self.h, a.ctypes.data_as(c_vp), a.size))
+
+    # distributed
+    def share(self):
+        _chk(self.L.iqsb_share(self.h))
+
+    def gate1_global(self, M, pos, m):
+        mm = _m(m)
+        _chk(self.L.iqsb_gate1_global(self.h, M, pos, mm.ctypes.data_as(c_vp)))
+
+    def cgate1_global(self, M, cpos, tpos, m):
+        mm = _m(m)
+        _chk(self.L.iqsb_cgate1_global(self.h, M, cpos, tpos, mm.ctypes.data_as(c_vp)))
+
+    def swap2x2_global(self, M, pos1, pos2, m):
+        mm = _m(m)
+        _chk(self.L.iqsb_swap2x2_global(self.h, M, pos1, pos2, mm.ctypes.data_as(c_vp)))
+
+    def permute_global(self, src_rank, dst_rank):
+        _chk(self.L.iqsb_permute_global(self.h, src_rank, dst_rank))

@@ -1,0 +1,399 @@
+// comm.cu -- the distributed half of the engine: one process per GPU, shards published to the
+// peers with cudaIpc, gates on global qubits executed by ONE kernel per rank that reads and
+// writes the partner's shard directly over NVLink (no tmp buffer, no send/recv phases).
+//
+// Reference code replaced:
+//   HP_Distrpair(P)      src/qureg_apply1qubitgate.cpp:18-169   (4 MPI_Sendrecv + Loop_SN per chunk)
+//   HP_Distrpair(C,T)    src/qureg_applyctrl1qubitgate.cpp:24-220
+//   HP_DistrSwap         src/qureg_applyswap.cpp:247-480
+//   PermuteGlobalQubits  src/qureg_permute.cpp:149-185
+//   MPI_Allreduce_x / MPI_Bcast_x / barriers  include/mpi_utils.hpp:34-78, src/mpi_env.cpp:499-509
+//
+// Work split (same as the reference's i-task / j-task split, but without the exchange phases):
+// a pair (a_k on the rank whose target bit is 0, b_k on the rank whose bit is 1) is owned by
+// exactly one of the two ranks, chosen by one local "split" bit of k, so every pair is updated
+// in place by one thread: that thread loads one local and one remote amplitude chunk and
+// stores both.  Per rank and per direction the link carries 16 B x (pairs/2) of loads and the
+// same amount of stores in the opposite direction, i.e. the algorithmic 16*L bytes for a dense
+// 1-qubit gate on a global qubit.
+//
+// NCCL is used for the bootstrap (all-gather of IPC handles) and the scalar collectives.
+#include <nccl.h>
+#include <string.h>
+
+#include "iqsb_internal.cuh"
+
+#define IQSB_NCCL(call)                                                                      \
+  do {                                                                                       \
+    ncclResult_t r__ = (call);                                                               \
+    if (r__ != ncclSuccess) {                                                                \
+      iqsb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r__)); \
+      return IQSB_ERR_NCCL;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+struct iqsb_peer_table {
+  ncclComm_t comm = nullptr;
+  uint32_t *flags_local = nullptr;  // [nranks] on this GPU; slot r is written by rank r
+  uint32_t **flags_peer = nullptr;  // host array: peer-mapped pointer to every rank's flags
+  uint32_t **d_flags_peer = nullptr;
+  uint32_t epoch = 0;
+  double *d_coll = nullptr;  // staging for scalar collectives
+  void *d_handles = nullptr; // [nranks * 64] staging for handle all-gathers
+};
+
+namespace {
+
+constexpr int kMaxCollDoubles = 32;
+
+// Every rank stores `epoch` into slot `me` of every peer's flag array, then waits until all
+// of its own slots reached `epoch`.  Kernel boundaries on the stream order it after the
+// preceding gate kernel; the system fence publishes that kernel's peer stores first.
+__global__ void k_barrier(uint32_t *const *peer_flags, volatile uint32_t *my_flags, int me, int nranks, uint32_t epoch) {
+  int r = threadIdx.x;
+  if (r < nranks && r != me) {
+    __threadfence_system();
+    volatile uint32_t *dst = peer_flags[r] + me;
+    *dst = epoch;
+    __threadfence_system();
+    while ((int32_t)(my_flags[r] - epoch) < 0) {
+    }
+    __threadfence_system();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_copy_chunks(const Chunk<T> *__restrict__ src, Chunk<T> *__restrict__ dst, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * 256;
+  for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += stride) st_chunk(dst + t, ld_chunk(src + t));
+}
+
+}  // namespace
+
+static int allgather_bytes64(iqsb_ctx *ctx, const void *mine64, void *all_host) {
+  iqsb_peer_table *pt = ctx->peers;
+  IQSB_CUDA(cudaMemcpyAsync((char *)pt->d_handles + 64 * ctx->rank, mine64, 64, cudaMemcpyHostToDevice, ctx->stream));
+  IQSB_NCCL(ncclAllGather((char *)pt->d_handles + 64 * ctx->rank, pt->d_handles, 64, ncclChar, pt->comm, ctx->stream));
+  IQSB_CUDA(cudaMemcpyAsync(all_host, pt->d_handles, 64 * ctx->nranks, cudaMemcpyDeviceToHost, ctx->stream));
+  IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return IQSB_OK;
+}
+
+static int open_peers(iqsb_ctx *ctx, void *mine, void **out_ptrs) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  IQSB_CUDA(cudaIpcGetMemHandle(&h, mine));
+  cudaIpcMemHandle_t *all = new cudaIpcMemHandle_t[ctx->nranks];
+  int rc = allgather_bytes64(ctx, &h, all);
+  if (rc != IQSB_OK) { delete[] all; return rc; }
+  for (int r = 0; r < ctx->nranks; ++r) {
+    if (r == ctx->rank) { out_ptrs[r] = mine; continue; }
+    cudaError_t e = cudaIpcOpenMemHandle(&out_ptrs[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      iqsb_set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+      delete[] all;
+      return IQSB_ERR_CUDA;
+    }
+  }
+  delete[] all;
+  return IQSB_OK;
+}
+
+extern "C" int iqsb_unique_id(void *out_128_bytes) {
+  IQSB_REQUIRE(out_128_bytes, "iqsb_unique_id: null argument");
+  static_assert(sizeof(ncclUniqueId) == IQSB_UNIQUE_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  IQSB_NCCL(ncclGetUniqueId(&id));
+  memcpy(out_128_bytes, &id, sizeof(id));
+  return IQSB_OK;
+}
+
+int iqsb_comm_init(iqsb_ctx *ctx, const void *uid) {
+  iqsb_peer_table *pt = new iqsb_peer_table();
+  ctx->peers = pt;
+  ncclUniqueId id;
+  memcpy(&id, uid, sizeof(id));
+  IQSB_NCCL(ncclCommInitRank(&pt->comm, ctx->nranks, id, ctx->rank));
+  ctx->comm = pt->comm;
+  IQSB_CUDA(cudaMalloc(&pt->d_coll, sizeof(double) * kMaxCollDoubles));
+  IQSB_CUDA(cudaMalloc(&pt->d_handles, 64 * ctx->nranks));
+  IQSB_CUDA(cudaMalloc(&pt->flags_local, sizeof(uint32_t) * ctx->nranks));
+  IQSB_CUDA(cudaMemset(pt->flags_local, 0, sizeof(uint32_t) * ctx->nranks));
+  pt->flags_peer = new uint32_t *[ctx->nranks];
+  IQSB_TRY(open_peers(ctx, pt->flags_local, (void **)pt->flags_peer));
+  IQSB_CUDA(cudaMalloc(&pt->d_flags_peer, sizeof(uint32_t *) * ctx->nranks));
+  IQSB_CUDA(cudaMemcpy(pt->d_flags_peer, pt->flags_peer, sizeof(uint32_t *) * ctx->nranks, cudaMemcpyHostToDevice));
+  // nobody may signal before everyone has zeroed and mapped the flags
+  IQSB_NCCL(ncclAllReduce(pt->d_coll, pt->d_coll, 1, ncclDouble, ncclSum, pt->comm, ctx->stream));
+  IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return IQSB_OK;
+}
+
+int iqsb_comm_finalize(iqsb_ctx *ctx) {
+  iqsb_peer_table *pt = ctx->peers;
+  if (!pt) return IQSB_OK;
+  for (int r = 0; r < ctx->nranks; ++r)
+    if (r != ctx->rank && pt->flags_peer && pt->flags_peer[r]) cudaIpcCloseMemHandle(pt->flags_peer[r]);
+  if (pt->comm) ncclCommDestroy(pt->comm);
+  cudaFree(pt->d_coll);
+  cudaFree(pt->d_handles);
+  cudaFree(pt->flags_local);
+  cudaFree(pt->d_flags_peer);
+  delete[] pt->flags_peer;
+  delete pt;
+  ctx->peers = nullptr;
+  return IQSB_OK;
+}
+
+static int peer_barrier(iqsb_ctx *ctx) {
+  iqsb_peer_table *pt = ctx->peers;
+  pt->epoch++;
+  k_barrier<<<1, 32, 0, ctx->stream>>>(pt->d_flags_peer, pt->flags_local, ctx->rank, ctx->nranks, pt->epoch);
+  return iqsb_check_launch(ctx, "k_barrier");
+}
+
+extern "C" int iqsb_barrier(iqsb_ctx *ctx) {
+  IQSB_REQUIRE(ctx, "iqsb_barrier: null context");
+  if (ctx->nranks > 1) IQSB_TRY(peer_barrier(ctx));
+  IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return IQSB_OK;
+}
+
+extern "C" int iqsb_allreduce_f64(iqsb_ctx *ctx, double *inout, int n, int op) {
+  IQSB_REQUIRE(ctx && inout, "iqsb_allreduce_f64: null argument");
+  IQSB_REQUIRE(n >= 0 && n <= kMaxCollDoubles, "iqsb_allreduce_f64: at most %d values", kMaxCollDoubles);
+  if (ctx->nranks == 1 || n == 0) return IQSB_OK;
+  iqsb_peer_table *pt = ctx->peers;
+  IQSB_CUDA(cudaMemcpyAsync(pt->d_coll, inout, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  IQSB_NCCL(ncclAllReduce(pt->d_coll, pt->d_coll, n, ncclDouble, op == IQSB_MAX ? ncclMax : ncclSum, pt->comm, ctx->stream));
+  IQSB_CUDA(cudaMemcpyAsync(inout, pt->d_coll, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return IQSB_OK;
+}
+
+extern "C" int iqsb_bcast_f64(iqsb_ctx *ctx, double *inout, int n, int root) {
+  IQSB_REQUIRE(ctx && inout, "iqsb_bcast_f64: null argument");
+  IQSB_REQUIRE(n >= 0 && n <= kMaxCollDoubles, "iqsb_bcast_f64: at most %d values", kMaxCollDoubles);
+  IQSB_REQUIRE(root >= 0 && root < ctx->nranks, "iqsb_bcast_f64: bad root");
+  if (ctx->nranks == 1 || n == 0) return IQSB_OK;
+  iqsb_peer_table *pt = ctx->peers;
+  IQSB_CUDA(cudaMemcpyAsync(pt->d_coll, inout, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  IQSB_NCCL(ncclBroadcast(pt->d_coll, pt->d_coll, n, ncclDouble, root, pt->comm, ctx->stream));
+  IQSB_CUDA(cudaMemcpyAsync(inout, pt->d_coll, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return IQSB_OK;
+}
+
+extern "C" int iqsb_share(iqsb_state *st) {
+  IQSB_REQUIRE(st, "iqsb_share: null argument");
+  iqsb_ctx *ctx = st->ctx;
+  if (st->shared) return IQSB_OK;
+  st->peer_ptr = new void *[ctx->nranks];
+  for (int r = 0; r < ctx->nranks; ++r) st->peer_ptr[r] = nullptr;
+  st->peer_ptr[ctx->rank] = st->d;
+  if (ctx->nranks > 1) {
+    IQSB_REQUIRE(st->mem_kind == IQSB_MEM_DEVICE, "iqsb_share: only IQSB_MEM_DEVICE shards can be shared");
+    IQSB_TRY(open_peers(ctx, st->d, st->peer_ptr));
+  }
+  st->shared = true;
+  return IQSB_OK;
+}
+
+int iqsb_comm_unshare(iqsb_state *st) {
+  iqsb_ctx *ctx = st->ctx;
+  if (ctx->nranks > 1) {
+    // peers may still be reading this shard: rendezvous before unmapping / freeing
+    peer_barrier(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < ctx->nranks; ++r)
+      if (r != ctx->rank && st->peer_ptr[r]) cudaIpcCloseMemHandle(st->peer_ptr[r]);
+    peer_barrier(ctx);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  delete[] st->peer_ptr;
+  st->peer_ptr = nullptr;
+  st->shared = false;
+  return IQSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// global-qubit gates
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// Launch the two-pointer pair kernel on the subset {k : bits fixed as given} of the local
+// index space; s0/s1 are shard base pointers (possibly remote), off0/off1 extra amplitude
+// offsets added on each side (in amplitudes).
+int launch_split(iqsb_state *st, void *s0, void *s1, int nfix, const unsigned *pos, const unsigned *val,
+                 uint64_t extra0, uint64_t extra1, const double m[8]) {
+  unsigned p[3], v[3];
+  for (int i = 0; i < nfix; ++i) { p[i] = pos[i]; v[i] = val[i]; }
+  for (int i = 0; i < nfix; ++i)
+    for (int j = i + 1; j < nfix; ++j)
+      if (p[j] < p[i]) { unsigned t = p[i]; p[i] = p[j]; p[j] = t; t = v[i]; v[i] = v[j]; v[j] = t; }
+  uint64_t L = st->local_amps;
+  bool w1 = (nfix > 0 && p[0] == 0) || ((extra0 | extra1) & 1) || L < 2;
+  unsigned ins[3];
+  uint64_t fixed = 0;
+  if (w1) {
+    for (int i = 0; i < nfix; ++i) { ins[i] = p[i]; fixed |= (uint64_t)v[i] << p[i]; }
+    Geom g = make_geom(L >> nfix, nfix, ins, fixed + extra0, fixed + extra1);
+    return iqsb_launch_pairs(st, s0, s1, 1, g, m);
+  }
+  for (int i = 0; i < nfix; ++i) { ins[i] = p[i] - 1; fixed |= (uint64_t)v[i] << (p[i] - 1); }
+  Geom g = make_geom((L / 2) >> nfix, nfix, ins, fixed + extra0 / 2, fixed + extra1 / 2);
+  return iqsb_launch_pairs(st, s0, s1, 2, g, m);
+}
+
+// highest local bit that is not in `avoid` (or -1)
+int pick_split_bit(unsigned M, int avoid0, int avoid1) {
+  for (int b = (int)M - 1; b >= 0; --b)
+    if (b != avoid0 && b != avoid1) return b;
+  return -1;
+}
+
+}  // namespace
+
+extern "C" int iqsb_gate1_global(iqsb_state *st, unsigned M, unsigned pos, const double m[8]) {
+  IQSB_REQUIRE(st && m, "iqsb_gate1_global: null argument");
+  iqsb_ctx *ctx = st->ctx;
+  IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_gate1_global: register is not shared across ranks");
+  IQSB_REQUIRE(M == st->log2_local && pos >= M && (1u << (pos - M)) < (unsigned)ctx->nranks, "iqsb_gate1_global: bad position");
+  unsigned rb = pos - M;
+  int partner = ctx->rank ^ (1 << rb);
+  unsigned mybit = (ctx->rank >> rb) & 1;
+  void *s0 = mybit ? st->peer_ptr[partner] : st->d;  // side whose target bit is 0
+  void *s1 = mybit ? st->d : st->peer_ptr[partner];
+  IQSB_TRY(peer_barrier(ctx));
+  int sb = pick_split_bit(M, -1, -1);
+  int rc;
+  if (sb < 0) {  // one amplitude per rank: the bit-0 rank does the single pair
+    rc = mybit ? IQSB_OK : launch_split(st, s0, s1, 0, nullptr, nullptr, 0, 0, m);
+  } else {
+    unsigned p[1] = {(unsigned)sb}, v[1] = {mybit ? 0u : 1u};  // i-task takes the upper half (reference 1q.cpp:130-152)
+    rc = launch_split(st, s0, s1, 1, p, v, 0, 0, m);
+  }
+  IQSB_TRY(rc);
+  ctx->nvlink_bytes += st->local_amps * st->amp_bytes();
+  return peer_barrier(ctx);
+}
+
+extern "C" int iqsb_cgate1_global(iqsb_state *st, unsigned M, unsigned cpos, unsigned tpos, const double m[8]) {
+  IQSB_REQUIRE(st && m, "iqsb_cgate1_global: null argument");
+  iqsb_ctx *ctx = st->ctx;
+  IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_cgate1_global: register is not shared across ranks");
+  IQSB_REQUIRE(M == st->log2_local && cpos < M && tpos >= M && (1u << (tpos - M)) < (unsigned)ctx->nranks,
+               "iqsb_cgate1_global: need control local and target global");
+  unsigned rb = tpos - M;
+  int partner = ctx->rank ^ (1 << rb);
+  unsigned mybit = (ctx->rank >> rb) & 1;
+  void *s0 = mybit ? st->peer_ptr[partner] : st->d;
+  void *s1 = mybit ? st->d : st->peer_ptr[partner];
+  IQSB_TRY(peer_barrier(ctx));
+  int sb = pick_split_bit(M, (int)cpos, -1);
+  int rc;
+  if (sb < 0) {
+    unsigned p[1] = {cpos}, v[1] = {1};
+    rc = mybit ? IQSB_OK : launch_split(st, s0, s1, 1, p, v, 0, 0, m);
+  } else {
+    unsigned p[2] = {cpos, (unsigned)sb}, v[2] = {1, mybit ? 0u : 1u};
+    rc = launch_split(st, s0, s1, 2, p, v, 0, 0, m);
+  }
+  IQSB_TRY(rc);
+  ctx->nvlink_bytes += st->local_amps / 2 * st->amp_bytes();
+  return peer_barrier(ctx);
+}
+
+extern "C" int iqsb_swap2x2_global(iqsb_state *st, unsigned M, unsigned pos1, unsigned pos2, const double m[8]) {
+  IQSB_REQUIRE(st && m, "iqsb_swap2x2_global: null argument");
+  iqsb_ctx *ctx = st->ctx;
+  IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_swap2x2_global: register is not shared across ranks");
+  IQSB_REQUIRE(M == st->log2_local && pos1 < pos2 && pos2 >= M && (1u << (pos2 - M)) < (unsigned)ctx->nranks,
+               "iqsb_swap2x2_global: need pos1 < pos2, pos2 global");
+  IQSB_TRY(peer_barrier(ctx));
+  int rc = IQSB_OK;
+  if (pos1 < M) {
+    // i0 = base + 2^pos1 lives on the rank whose pos2 bit is 0 (A); i1 = base + 2^pos2 on its
+    // partner (B) at local index base.  (reference qureg_applyswap.cpp:170-206, 292-400)
+    unsigned rb = pos2 - M;
+    int partner = ctx->rank ^ (1 << rb);
+    unsigned mybit = (ctx->rank >> rb) & 1;
+    void *s0 = mybit ? st->peer_ptr[partner] : st->d;
+    void *s1 = mybit ? st->d : st->peer_ptr[partner];
+    int sb = pick_split_bit(M, (int)pos1, -1);
+    if (sb < 0) {
+      unsigned p[1] = {pos1}, v[1] = {0};
+      rc = mybit ? IQSB_OK : launch_split(st, s0, s1, 1, p, v, 1ull << pos1, 0, m);
+    } else {
+      unsigned p[2] = {pos1, (unsigned)sb}, v[2] = {0, mybit ? 0u : 1u};
+      rc = launch_split(st, s0, s1, 2, p, v, 1ull << pos1, 0, m);
+    }
+    ctx->nvlink_bytes += st->local_amps / 2 * st->amp_bytes();
+  } else {
+    unsigned r1 = pos1 - M, r2 = pos2 - M;
+    unsigned b1 = (ctx->rank >> r1) & 1, b2 = (ctx->rank >> r2) & 1;
+    if (b1 != b2) {
+      int partner = ctx->rank ^ (1 << r1) ^ (1 << r2);
+      bool iamA = (b1 == 1);  // A holds i0 (pos1 bit 1, pos2 bit 0)
+      void *s0 = iamA ? st->d : st->peer_ptr[partner];
+      void *s1 = iamA ? st->peer_ptr[partner] : st->d;
+      int sb = pick_split_bit(M, -1, -1);
+      if (sb < 0) {
+        rc = iamA ? launch_split(st, s0, s1, 0, nullptr, nullptr, 0, 0, m) : IQSB_OK;
+      } else {
+        unsigned p[1] = {(unsigned)sb}, v[1] = {iamA ? 1u : 0u};
+        rc = launch_split(st, s0, s1, 1, p, v, 0, 0, m);
+      }
+      ctx->nvlink_bytes += st->local_amps * st->amp_bytes();
+    }
+  }
+  IQSB_TRY(rc);
+  return peer_barrier(ctx);
+}
+
+extern "C" int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank) {
+  IQSB_REQUIRE(st, "iqsb_permute_global: null argument");
+  iqsb_ctx *ctx = st->ctx;
+  IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_permute_global: register is not shared across ranks");
+  IQSB_REQUIRE(src_rank >= 0 && src_rank < ctx->nranks && dst_rank >= 0 && dst_rank < ctx->nranks, "iqsb_permute_global: bad ranks");
+  // Every shard is both a source and a destination, so the move is staged through the tmp area
+  // in chunks (as the reference does, qureg_permute.cpp:174-185), pulling with peer loads.
+  uint64_t L = st->local_amps, chunk = st->tmp_amps;
+  void *stage = (char *)st->d + L * st->amp_bytes();
+  void *owned = nullptr;
+  if (chunk == 0) {
+    chunk = L < (1ull << 26) ? L : (1ull << 26);
+    IQSB_CUDA(cudaMalloc(&owned, chunk * st->amp_bytes()));
+    stage = owned;
+  }
+  if (chunk > L) chunk = L;
+  IQSB_REQUIRE(chunk >= 2 && L % chunk == 0, "iqsb_permute_global: tmp size must divide the shard");
+  int rc = IQSB_OK;
+  int grid = ctx->num_sms * 8;
+  for (uint64_t c = 0; c < L && rc == IQSB_OK; c += chunk) {
+    rc = peer_barrier(ctx);  // sources are final up to here
+    if (rc != IQSB_OK) break;
+    const char *src = (const char *)st->peer_ptr[src_rank] + c * st->amp_bytes();
+    char *mine = (char *)st->d + c * st->amp_bytes();
+    if (st->dtype == IQSB_F64)
+      k_copy_chunks<double><<<grid, 256, 0, ctx->stream>>>((const Chunk<double> *)src, (Chunk<double> *)stage, chunk / 2);
+    else
+      k_copy_chunks<float><<<grid, 256, 0, ctx->stream>>>((const Chunk<float> *)src, (Chunk<float> *)stage, chunk / 2);
+    rc = iqsb_check_launch(ctx, "k_copy_chunks");
+    if (rc != IQSB_OK) break;
+    rc = peer_barrier(ctx);  // everybody has pulled chunk c: it may be overwritten
+    if (rc != IQSB_OK) break;
+    if (st->dtype == IQSB_F64)
+      k_copy_chunks<double><<<grid, 256, 0, ctx->stream>>>((const Chunk<double> *)stage, (Chunk<double> *)mine, chunk / 2);
+    else
+      k_copy_chunks<float><<<grid, 256, 0, ctx->stream>>>((const Chunk<float> *)stage, (Chunk<float> *)mine, chunk / 2);
+    rc = iqsb_check_launch(ctx, "k_copy_chunks");
+  }
+  if (rc == IQSB_OK && src_rank != ctx->rank) ctx->nvlink_bytes += L * st->amp_bytes();
+  if (rc == IQSB_OK) rc = peer_barrier(ctx);
+  if (owned) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(owned);
+  }
+  return rc;
+}

@@ -1,0 +1,538 @@
+// kernels_gate.cu -- the gate loops of Intel-QS as sm_100a kernels.
+//
+// Reference loops replaced (all HBM-bound, ~0.44 flop/B):
+//   Loop_DN  src/highperfkernels.cpp:287-380  -> k_pairs   (one inserted bit)
+//   Loop_TN  src/highperfkernels.cpp:397-486  -> k_pairs   (two inserted bits)
+//   Loop_SN  src/highperfkernels.cpp:192-240  -> k_pairs   (two base pointers; peer memory)
+//   ScaleState src/highperfkernels.cpp:501-520 -> k_scale_subset
+//   ApplyDiag loops src/qureg_applydiag.cpp:157-224 -> k_diag2
+//   Apply2QubitGate src/qureg_apply2qubitgate.cpp:47-65 -> k_quads
+//
+// Every kernel enumerates a subset of the index space described by a Geom (zero bits inserted
+// at up to three positions) so one code path serves local, controlled, swap-family and
+// distributed (split) variants.  Width 2 kernels move 32-byte chunks (two amplitudes) with
+// 256-bit loads/stores; width 1 kernels (a special bit sits at position 0) move 16 bytes.
+#include "iqsb_internal.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kUnroll = 2;  // work items per thread, all loads issued before any store
+
+__host__ __device__ inline uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+// ---- pairs, width 2: each partner is a chunk of two amplitudes ------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+    k_pairs_w2(Chunk<T> *s0, Chunk<T> *s1, Geom g, Mat2<T> m) {
+  uint64_t t0 = ((uint64_t)blockIdx.x * kUnroll) * kBlock + threadIdx.x;
+  Chunk<T> v0[kUnroll], v1[kUnroll];
+  uint64_t i0[kUnroll], i1[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      uint64_t x = expand(t, g);
+      i0[u] = x + g.off0;
+      i1[u] = x + g.off1;
+      v0[u] = ld_chunk(s0 + i0[u]);
+      v1[u] = ld_chunk(s1 + i1[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      apply2x2(m, v0[u].a, v1[u].a);
+      apply2x2(m, v0[u].b, v1[u].b);
+      st_chunk(s0 + i0[u], v0[u]);
+      st_chunk(s1 + i1[u], v1[u]);
+    }
+  }
+}
+
+// ---- pairs, width 1: each partner is a single amplitude -------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+    k_pairs_w1(Cx<T> *s0, Cx<T> *s1, Geom g, Mat2<T> m) {
+  uint64_t t0 = ((uint64_t)blockIdx.x * kUnroll) * kBlock + threadIdx.x;
+  Cx<T> v0[kUnroll], v1[kUnroll];
+  uint64_t i0[kUnroll], i1[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      uint64_t x = expand(t, g);
+      i0[u] = x + g.off0;
+      i1[u] = x + g.off1;
+      v0[u] = ld_amp(s0 + i0[u]);
+      v1[u] = ld_amp(s1 + i1[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      apply2x2(m, v0[u], v1[u]);
+      st_amp(s0 + i0[u], v0[u]);
+      st_amp(s1 + i1[u], v1[u]);
+    }
+  }
+}
+
+// ---- target position 0: both partners live in one chunk -------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_inchunk(Chunk<T> *__restrict__ s, Geom g, Mat2<T> m) {
+  constexpr int U = 2 * kUnroll;
+  uint64_t t0 = ((uint64_t)blockIdx.x * U) * kBlock + threadIdx.x;
+  Chunk<T> v[U];
+  uint64_t i[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      i[u] = expand(t, g) + g.off0;
+      v[u] = ld_chunk(s + i[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      apply2x2(m, v[u].a, v[u].b);
+      st_chunk(s + i[u], v[u]);
+    }
+  }
+}
+
+// ---- amp *= f on a subset --------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_scale_w2(Chunk<T> *__restrict__ s, Geom g, Cx<T> f) {
+  constexpr int U = 2 * kUnroll;
+  uint64_t t0 = ((uint64_t)blockIdx.x * U) * kBlock + threadIdx.x;
+  Chunk<T> v[U];
+  uint64_t i[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      i[u] = expand(t, g) + g.off0;
+      v[u] = ld_chunk(s + i[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      v[u].a = cmul(v[u].a, f);
+      v[u].b = cmul(v[u].b, f);
+      st_chunk(s + i[u], v[u]);
+    }
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_scale_w1(Cx<T> *__restrict__ s, Geom g, Cx<T> f) {
+  constexpr int U = 2 * kUnroll;
+  uint64_t t0 = ((uint64_t)blockIdx.x * U) * kBlock + threadIdx.x;
+  Cx<T> v[U];
+  uint64_t i[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      i[u] = expand(t, g) + g.off0;
+      v[u] = ld_amp(s + i[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      v[u] = cmul(v[u], f);
+      st_amp(s + i[u], v[u]);
+    }
+  }
+}
+
+// ---- amp = 0 on a subset (CollapseQubit) ----------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_zero_w2(Chunk<T> *__restrict__ s, Geom g) {
+  uint64_t t = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (t < g.nwork) {
+    Chunk<T> z;
+    z.a = {T(0), T(0)};
+    z.b = {T(0), T(0)};
+    st_chunk(s + expand(t, g) + g.off0, z);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_zero_w1(Cx<T> *__restrict__ s, Geom g) {
+  uint64_t t = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (t < g.nwork) {
+    Cx<T> z = {T(0), T(0)};
+    st_amp(s + expand(t, g) + g.off0, z);
+  }
+}
+
+// ---- ApplyDiag: amp *= d[2*bit(pos1) + bit(pos2)], one pass ---------------------------
+template <typename T>
+struct Diag4 {
+  Cx<T> d[4];
+};
+// bit selectors are given on the amplitude index; sel = 64 means "use the constant bit"
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+    k_diag2(Chunk<T> *__restrict__ s, uint64_t nchunks, unsigned p1, unsigned p2, unsigned c1,
+            unsigned c2, Diag4<T> d) {
+  constexpr int U = 2 * kUnroll;
+  uint64_t t0 = ((uint64_t)blockIdx.x * U) * kBlock + threadIdx.x;
+  Chunk<T> v[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < nchunks) v[u] = ld_chunk(s + t);
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < nchunks) {
+      uint64_t ia = 2 * t, ib = 2 * t + 1;
+      unsigned a1 = p1 < 64 ? (unsigned)((ia >> p1) & 1) : c1;
+      unsigned a2 = p2 < 64 ? (unsigned)((ia >> p2) & 1) : c2;
+      unsigned b1 = p1 < 64 ? (unsigned)((ib >> p1) & 1) : c1;
+      unsigned b2 = p2 < 64 ? (unsigned)((ib >> p2) & 1) : c2;
+      v[u].a = cmul(v[u].a, d.d[2 * a1 + a2]);
+      v[u].b = cmul(v[u].b, d.d[2 * b1 + b2]);
+      st_chunk(s + t, v[u]);
+    }
+  }
+}
+
+// ---- Apply2QubitGate: 4x4 on quads -----------------------------------------------------
+template <typename T>
+struct Mat4 {
+  Cx<T> m[4][4];
+};
+template <typename T>
+__device__ __forceinline__ void apply4x4(const Mat4<T> &m, Cx<T> (&a)[4]) {
+  Cx<T> in[4] = {a[0], a[1], a[2], a[3]};
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    // ((m0*uu + m1*ud) + m2*du) + m3*dd   (reference qureg_apply2qubitgate.cpp:60-61)
+    Cx<T> acc = cadd(cmul(m.m[r][0], in[0]), cmul(m.m[r][1], in[1]));
+    acc = cadd(acc, cmul(m.m[r][2], in[2]));
+    acc = cadd(acc, cmul(m.m[r][3], in[3]));
+    a[r] = acc;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+    k_quads_w2(Chunk<T> *__restrict__ s, Geom g, uint64_t dl, uint64_t dh, Mat4<T> m) {
+  uint64_t t = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (t >= g.nwork) return;
+  uint64_t x = expand(t, g);
+  Chunk<T> c[4];
+  c[0] = ld_chunk(s + x);
+  c[1] = ld_chunk(s + x + dl);
+  c[2] = ld_chunk(s + x + dh);
+  c[3] = ld_chunk(s + x + dh + dl);
+  Cx<T> a[4] = {c[0].a, c[1].a, c[2].a, c[3].a};
+  Cx<T> b[4] = {c[0].b, c[1].b, c[2].b, c[3].b};
+  apply4x4(m, a);
+  apply4x4(m, b);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    c[r].a = a[r];
+    c[r].b = b[r];
+  }
+  st_chunk(s + x, c[0]);
+  st_chunk(s + x + dl, c[1]);
+  st_chunk(s + x + dh, c[2]);
+  st_chunk(s + x + dh + dl, c[3]);
+}
+// one of the two positions is 0: the chunk holds (low=0, low=1) for position-0-is-low, or
+// (high=0, high=1) when position 0 is the high qubit.
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+    k_quads_p0(Chunk<T> *__restrict__ s, Geom g, uint64_t dother, int zero_is_low, Mat4<T> m) {
+  uint64_t t = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (t >= g.nwork) return;
+  uint64_t x = expand(t, g);
+  Chunk<T> c0 = ld_chunk(s + x), c1 = ld_chunk(s + x + dother);
+  Cx<T> a[4];
+  if (zero_is_low) {  // t = 2*bit(other) + bit(0)
+    a[0] = c0.a; a[1] = c0.b; a[2] = c1.a; a[3] = c1.b;
+  } else {            // t = 2*bit(0) + bit(other)
+    a[0] = c0.a; a[1] = c1.a; a[2] = c0.b; a[3] = c1.b;
+  }
+  apply4x4(m, a);
+  if (zero_is_low) {
+    c0.a = a[0]; c0.b = a[1]; c1.a = a[2]; c1.b = a[3];
+  } else {
+    c0.a = a[0]; c1.a = a[1]; c0.b = a[2]; c1.b = a[3];
+  }
+  st_chunk(s + x, c0);
+  st_chunk(s + x + dother, c1);
+}
+
+template <typename T>
+Cx<T> make_cx(const double f[2]) {
+  return Cx<T>{(T)f[0], (T)f[1]};
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------
+int iqsb_launch_pairs(iqsb_state *st, void *s0, void *s1, int width, const Geom &g, const double m[8]) {
+  if (g.nwork == 0) return IQSB_OK;
+  iqsb_ctx *ctx = st->ctx;
+  unsigned grid = (unsigned)div_up(g.nwork, (uint64_t)kBlock * kUnroll);
+  if (st->dtype == IQSB_F64) {
+    if (width == 2)
+      k_pairs_w2<double><<<grid, kBlock, 0, ctx->stream>>>((Chunk<double> *)s0, (Chunk<double> *)s1, g,
+                                                          make_mat<double>(m));
+    else
+      k_pairs_w1<double><<<grid, kBlock, 0, ctx->stream>>>((Cx<double> *)s0, (Cx<double> *)s1, g,
+                                                          make_mat<double>(m));
+  } else {
+    if (width == 2)
+      k_pairs_w2<float><<<grid, kBlock, 0, ctx->stream>>>((Chunk<float> *)s0, (Chunk<float> *)s1, g,
+                                                         make_mat<float>(m));
+    else
+      k_pairs_w1<float><<<grid, kBlock, 0, ctx->stream>>>((Cx<float> *)s0, (Cx<float> *)s1, g,
+                                                         make_mat<float>(m));
+  }
+  return iqsb_check_launch(ctx, "k_pairs");
+}
+
+int iqsb_launch_inchunk(iqsb_state *st, void *s, const Geom &g, const double m[8]) {
+  if (g.nwork == 0) return IQSB_OK;
+  iqsb_ctx *ctx = st->ctx;
+  unsigned grid = (unsigned)div_up(g.nwork, (uint64_t)kBlock * 2 * kUnroll);
+  if (st->dtype == IQSB_F64)
+    k_inchunk<double><<<grid, kBlock, 0, ctx->stream>>>((Chunk<double> *)s, g, make_mat<double>(m));
+  else
+    k_inchunk<float><<<grid, kBlock, 0, ctx->stream>>>((Chunk<float> *)s, g, make_mat<float>(m));
+  return iqsb_check_launch(ctx, "k_inchunk");
+}
+
+int iqsb_launch_scale_subset(iqsb_state *st, void *s, int width, const Geom &g, const double f[2]) {
+  if (g.nwork == 0) return IQSB_OK;
+  iqsb_ctx *ctx = st->ctx;
+  unsigned grid = (unsigned)div_up(g.nwork, (uint64_t)kBlock * 2 * kUnroll);
+  if (st->dtype == IQSB_F64) {
+    if (width == 2)
+      k_scale_w2<double><<<grid, kBlock, 0, ctx->stream>>>((Chunk<double> *)s, g, make_cx<double>(f));
+    else
+      k_scale_w1<double><<<grid, kBlock, 0, ctx->stream>>>((Cx<double> *)s, g, make_cx<double>(f));
+  } else {
+    if (width == 2)
+      k_scale_w2<float><<<grid, kBlock, 0, ctx->stream>>>((Chunk<float> *)s, g, make_cx<float>(f));
+    else
+      k_scale_w1<float><<<grid, kBlock, 0, ctx->stream>>>((Cx<float> *)s, g, make_cx<float>(f));
+  }
+  return iqsb_check_launch(ctx, "k_scale");
+}
+
+int iqsb_launch_zero_subset(iqsb_state *st, void *s, int width, const Geom &g) {
+  if (g.nwork == 0) return IQSB_OK;
+  iqsb_ctx *ctx = st->ctx;
+  unsigned grid = (unsigned)div_up(g.nwork, (uint64_t)kBlock);
+  if (st->dtype == IQSB_F64) {
+    if (width == 2)
+      k_zero_w2<double><<<grid, kBlock, 0, ctx->stream>>>((Chunk<double> *)s, g);
+    else
+      k_zero_w1<double><<<grid, kBlock, 0, ctx->stream>>>((Cx<double> *)s, g);
+  } else {
+    if (width == 2)
+      k_zero_w2<float><<<grid, kBlock, 0, ctx->stream>>>((Chunk<float> *)s, g);
+    else
+      k_zero_w1<float><<<grid, kBlock, 0, ctx->stream>>>((Cx<float> *)s, g);
+  }
+  return iqsb_check_launch(ctx, "k_zero");
+}
+
+// ---------------------------------------------------------------------------------------
+// C ABI: local gates
+// ---------------------------------------------------------------------------------------
+static inline char *amp_ptr(iqsb_state *st, uint64_t first_amp) {
+  return (char *)st->d + first_amp * st->amp_bytes();
+}
+
+extern "C" int iqsb_gate1(iqsb_state *st, unsigned pos, const double m[8], uint64_t sind, uint64_t eind) {
+  IQSB_REQUIRE(st && m, "iqsb_gate1: null argument");
+  IQSB_REQUIRE(pos < st->log2_local, "iqsb_gate1: position %u is not local (M=%u)", pos, st->log2_local);
+  IQSB_REQUIRE(sind <= eind && eind <= st->local_amps, "iqsb_gate1: bad range");
+  uint64_t count = eind - sind, blk = 2ull << pos;
+  IQSB_REQUIRE(sind % blk == 0 && count % blk == 0, "iqsb_gate1: range not aligned to 2^(pos+1)");
+  if (pos == 0) {
+    Geom g = make_geom(count / 2, 0, nullptr, 0, 0);
+    return iqsb_launch_inchunk(st, amp_ptr(st, sind), g, m);
+  }
+  unsigned ins[1] = {pos - 1};
+  Geom g = make_geom(count / 4, 1, ins, 0, 1ull << (pos - 1));
+  char *p = amp_ptr(st, sind);
+  return iqsb_launch_pairs(st, p, p, 2, g, m);
+}
+
+extern "C" int iqsb_cgate1(iqsb_state *st, unsigned cpos, unsigned tpos, const double m[8],
+                           uint64_t sind, uint64_t eind) {
+  IQSB_REQUIRE(st && m, "iqsb_cgate1: null argument");
+  IQSB_REQUIRE(cpos != tpos, "iqsb_cgate1: control == target");
+  IQSB_REQUIRE(cpos < st->log2_local && tpos < st->log2_local, "iqsb_cgate1: positions must be local");
+  IQSB_REQUIRE(sind <= eind && eind <= st->local_amps, "iqsb_cgate1: bad range");
+  unsigned hi = cpos > tpos ? cpos : tpos;
+  uint64_t count = eind - sind, blk = 2ull << hi;
+  IQSB_REQUIRE(sind % blk == 0 && count % blk == 0, "iqsb_cgate1: range not aligned to 2^(max pos+1)");
+  char *p = amp_ptr(st, sind);
+  if (tpos == 0) {  // partners share a chunk; chunk index must have bit (cpos-1) set
+    unsigned ins[1] = {cpos - 1};
+    Geom g = make_geom(count / 4, 1, ins, 1ull << (cpos - 1), 0);
+    return iqsb_launch_inchunk(st, p, g, m);
+  }
+  if (cpos == 0) {  // only odd amplitudes take part: 16-byte accesses
+    unsigned ins[2] = {0, tpos};
+    Geom g = make_geom(count / 4, 2, ins, 1, 1 | (1ull << tpos));
+    return iqsb_launch_pairs(st, p, p, 1, g, m);
+  }
+  unsigned lo = cpos < tpos ? cpos : tpos;
+  unsigned ins[2] = {lo - 1, hi - 1};
+  uint64_t cbit = 1ull << (cpos - 1), tbit = 1ull << (tpos - 1);
+  Geom g = make_geom(count / 8, 2, ins, cbit, cbit | tbit);
+  return iqsb_launch_pairs(st, p, p, 2, g, m);
+}
+
+extern "C" int iqsb_swap2x2(iqsb_state *st, unsigned pos1, unsigned pos2, const double m[8]) {
+  IQSB_REQUIRE(st && m, "iqsb_swap2x2: null argument");
+  IQSB_REQUIRE(pos1 < pos2 && pos2 < st->log2_local, "iqsb_swap2x2: need pos1 < pos2 < M");
+  uint64_t L = st->local_amps;
+  if (pos1 == 0) {
+    unsigned ins[2] = {0, pos2};
+    Geom g = make_geom(L / 4, 2, ins, 1, 1ull << pos2);
+    return iqsb_launch_pairs(st, st->d, st->d, 1, g, m);
+  }
+  unsigned ins[2] = {pos1 - 1, pos2 - 1};
+  Geom g = make_geom(L / 8, 2, ins, 1ull << (pos1 - 1), 1ull << (pos2 - 1));
+  return iqsb_launch_pairs(st, st->d, st->d, 2, g, m);
+}
+
+extern "C" int iqsb_scale(iqsb_state *st, const double s[2], uint64_t start, uint64_t end) {
+  IQSB_REQUIRE(st && s, "iqsb_scale: null argument");
+  IQSB_REQUIRE(start <= end && end <= st->local_amps, "iqsb_scale: bad range");
+  if (s[0] == 1.0 && s[1] == 0.0) return IQSB_OK;  // reference highperfkernels.cpp:505
+  uint64_t count = end - start;
+  if ((start | count) & 1) {
+    Geom g = make_geom(count, 0, nullptr, 0, 0);
+    return iqsb_launch_scale_subset(st, amp_ptr(st, start), 1, g, s);
+  }
+  Geom g = make_geom(count / 2, 0, nullptr, 0, 0);
+  return iqsb_launch_scale_subset(st, amp_ptr(st, start), 2, g, s);
+}
+
+// scale the amplitudes whose local bits satisfy (bit[pos[k]] == val[k]) for k < nfix by f
+static int scale_where(iqsb_state *st, int nfix, const unsigned *pos, const unsigned *val, const double f[2]) {
+  if (f[0] == 1.0 && f[1] == 0.0) return IQSB_OK;
+  // sort ascending
+  unsigned p[3], v[3];
+  for (int i = 0; i < nfix; ++i) { p[i] = pos[i]; v[i] = val[i]; }
+  for (int i = 0; i < nfix; ++i)
+    for (int j = i + 1; j < nfix; ++j)
+      if (p[j] < p[i]) { unsigned t = p[i]; p[i] = p[j]; p[j] = t; t = v[i]; v[i] = v[j]; v[j] = t; }
+  bool w1 = nfix > 0 && p[0] == 0;
+  if (st->local_amps < 2) w1 = true;
+  uint64_t off = 0;
+  unsigned ins[3];
+  if (w1) {
+    for (int i = 0; i < nfix; ++i) { ins[i] = p[i]; off |= (uint64_t)v[i] << p[i]; }
+    Geom g = make_geom(st->local_amps >> nfix, nfix, ins, off, 0);
+    return iqsb_launch_scale_subset(st, st->d, 1, g, f);
+  }
+  for (int i = 0; i < nfix; ++i) { ins[i] = p[i] - 1; off |= (uint64_t)v[i] << (p[i] - 1); }
+  Geom g = make_geom((st->local_amps / 2) >> nfix, nfix, ins, off, 0);
+  return iqsb_launch_scale_subset(st, st->d, 2, g, f);
+}
+
+extern "C" int iqsb_phase_by_bit(iqsb_state *st, int cpos, unsigned pos, const double d0[2],
+                                 const double d1[2]) {
+  IQSB_REQUIRE(st && d0 && d1, "iqsb_phase_by_bit: null argument");
+  IQSB_REQUIRE(pos < st->log2_local && cpos < (int)st->log2_local && cpos != (int)pos,
+               "iqsb_phase_by_bit: bad positions");
+  unsigned p[2], v[2];
+  int nfix = 0;
+  if (cpos >= 0) { p[nfix] = (unsigned)cpos; v[nfix] = 1; ++nfix; }
+  p[nfix] = pos;
+  v[nfix] = 0;
+  IQSB_TRY(scale_where(st, nfix + 1, p, v, d0));
+  v[nfix] = 1;
+  return scale_where(st, nfix + 1, p, v, d1);
+}
+
+extern "C" int iqsb_collapse(iqsb_state *st, unsigned pos, int value) {
+  IQSB_REQUIRE(st, "iqsb_collapse: null argument");
+  IQSB_REQUIRE(pos < st->log2_local, "iqsb_collapse: position must be local");
+  // zero the half whose bit `pos` differs from `value` (reference qureg_measure.cpp:107-111)
+  uint64_t kill = value ? 0 : 1;
+  if (pos == 0) {
+    unsigned ins[1] = {0};
+    Geom g = make_geom(st->local_amps / 2, 1, ins, kill, 0);
+    return iqsb_launch_zero_subset(st, st->d, 1, g);
+  }
+  unsigned ins[1] = {pos - 1};
+  Geom g = make_geom(st->local_amps / 4, 1, ins, kill << (pos - 1), 0);
+  return iqsb_launch_zero_subset(st, st->d, 2, g);
+}
+
+extern "C" int iqsb_diag2(iqsb_state *st, unsigned pos1, unsigned pos2, const double d[8], uint64_t glb_start) {
+  IQSB_REQUIRE(st && d, "iqsb_diag2: null argument");
+  IQSB_REQUIRE(pos1 != pos2 && pos1 < 64 && pos2 < 64, "iqsb_diag2: bad positions");
+  IQSB_REQUIRE(st->local_amps >= 2, "iqsb_diag2: shard too small");
+  iqsb_ctx *ctx = st->ctx;
+  unsigned M = st->log2_local;
+  unsigned p1 = pos1 < M ? pos1 : 64, p2 = pos2 < M ? pos2 : 64;
+  unsigned c1 = pos1 < M ? 0 : (unsigned)((glb_start >> pos1) & 1);
+  unsigned c2 = pos2 < M ? 0 : (unsigned)((glb_start >> pos2) & 1);
+  uint64_t nchunks = st->local_amps / 2;
+  unsigned grid = (unsigned)div_up(nchunks, (uint64_t)kBlock * 2 * kUnroll);
+  if (st->dtype == IQSB_F64) {
+    Diag4<double> dd;
+    for (int i = 0; i < 4; ++i) dd.d[i] = {d[2 * i], d[2 * i + 1]};
+    k_diag2<double><<<grid, kBlock, 0, ctx->stream>>>((Chunk<double> *)st->d, nchunks, p1, p2, c1, c2, dd);
+  } else {
+    Diag4<float> dd;
+    for (int i = 0; i < 4; ++i) dd.d[i] = {(float)d[2 * i], (float)d[2 * i + 1]};
+    k_diag2<float><<<grid, kBlock, 0, ctx->stream>>>((Chunk<float> *)st->d, nchunks, p1, p2, c1, c2, dd);
+  }
+  return iqsb_check_launch(ctx, "k_diag2");
+}
+
+template <typename T>
+static int launch_gate2(iqsb_state *st, unsigned ph, unsigned pl, const double m[32]) {
+  iqsb_ctx *ctx = st->ctx;
+  Mat4<T> mm;
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) mm.m[r][c] = {(T)m[2 * (4 * r + c)], (T)m[2 * (4 * r + c) + 1]};
+  unsigned lo = ph < pl ? ph : pl, hi = ph < pl ? pl : ph;
+  uint64_t L = st->local_amps;
+  if (lo == 0) {
+    unsigned ins[1] = {hi - 1};
+    Geom g = make_geom(L / 4, 1, ins, 0, 0);
+    unsigned grid = (unsigned)div_up(g.nwork, kBlock);
+    k_quads_p0<T><<<grid, kBlock, 0, ctx->stream>>>((Chunk<T> *)st->d, g, 1ull << (hi - 1), pl == 0 ? 1 : 0, mm);
+  } else {
+    unsigned ins[2] = {lo - 1, hi - 1};
+    Geom g = make_geom(L / 8, 2, ins, 0, 0);
+    unsigned grid = (unsigned)div_up(g.nwork, kBlock);
+    k_quads_w2<T><<<grid, kBlock, 0, ctx->stream>>>((Chunk<T> *)st->d, g, 1ull << (pl - 1), 1ull << (ph - 1), mm);
+  }
+  return iqsb_check_launch(ctx, "k_quads");
+}
+
+extern "C" int iqsb_gate2(iqsb_state *st, unsigned pos_high, unsigned pos_low, const double m[32]) {
+  IQSB_REQUIRE(st && m, "iqsb_gate2: null argument");
+  IQSB_REQUIRE(pos_high != pos_low && pos_high < st->log2_local && pos_low < st->log2_local,
+               "iqsb_gate2: positions must be distinct and local");
+  return st->dtype == IQSB_F64 ? launch_gate2<double>(st, pos_high, pos_low, m)
+                               : launch_gate2<float>(st, pos_high, pos_low, m);
+}

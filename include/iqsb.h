@@ -67,6 +67,10 @@ uint64_t iqsb_launch_count(const iqsb_ctx *ctx);
 /* device-side timing on the context's stream (CUDA events). */
 int iqsb_timer_start(iqsb_ctx *ctx);
 int iqsb_timer_stop(iqsb_ctx *ctx, double *elapsed_ms);
+/* numbered CUDA events on the context's stream (slot < 4096): record now, read the elapsed time
+ * between two recorded slots later (the call synchronises on the later event). */
+int iqsb_event_record(iqsb_ctx *ctx, int slot);
+int iqsb_event_elapsed(iqsb_ctx *ctx, int slot_from, int slot_to, double *elapsed_ms);
 
 /* ---- scalar collectives: replace MPI_Allreduce_x / MPI_Bcast_x / MPI_Barrier
  *      (include/mpi_utils.hpp:34-78, src/mpi_env.cpp:499-509) ------------------------- */
@@ -181,6 +185,9 @@ int iqsb_gate1_global(iqsb_state *st, unsigned M, unsigned pos, const double m[8
 int iqsb_cgate1_global(iqsb_state *st, unsigned M, unsigned cpos, unsigned tpos, const double m[8]);
 /* swap-family gate with pos1 < pos2, pos2 >= M: replaces HP_DistrSwap (src/qureg_applyswap.cpp:247-480) */
 int iqsb_swap2x2_global(iqsb_state *st, unsigned M, unsigned pos1, unsigned pos2, const double m[8]);
+/* take part in a global-qubit step without owning pairs (ranks whose global control bit is 0,
+ * src/qureg_applyctrl1qubitgate.cpp:359-380): same two rendezvous as the gate itself. */
+int iqsb_idle_global(iqsb_state *st);
 /* whole-shard move: this rank's shard goes to `dst_rank`, it receives `src_rank`'s:
  * replaces the Sendrecv loop of PermuteGlobalQubits (src/qureg_permute.cpp:174-185) */
 int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank);

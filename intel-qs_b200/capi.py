@@ -51,6 +51,7 @@ def load():
         "iqsb_set_stream": [c_vp, c_vp], "iqsb_get_stream": [c_vp],
         "iqsb_launch_count": [c_vp], "iqsb_nvlink_bytes": [c_vp],
         "iqsb_timer_start": [c_vp], "iqsb_timer_stop": [c_vp, ctypes.POINTER(c_dbl)],
+        "iqsb_event_record": [c_vp, c_int], "iqsb_event_elapsed": [c_vp, c_int, c_int, ctypes.POINTER(c_dbl)],
         "iqsb_allreduce_f64": [c_vp, c_vp, c_int, c_int],
         "iqsb_bcast_f64": [c_vp, c_vp, c_int, c_int],
         "iqsb_barrier": [c_vp],
@@ -87,6 +88,7 @@ def load():
         "iqsb_axpy": [c_vp, c_vp, c_vp],
         "iqsb_permute_local": [c_vp, c_vp, c_uint],
         "iqsb_share": [c_vp],
+        "iqsb_idle_global": [c_vp],
         "iqsb_gate1_global": [c_vp, c_uint, c_uint, c_vp],
         "iqsb_cgate1_global": [c_vp, c_uint, c_uint, c_uint, c_vp],
         "iqsb_swap2x2_global": [c_vp, c_uint, c_uint, c_uint, c_vp],
@@ -158,6 +160,14 @@ class Context:
     def timer_stop(self):
         ms = c_dbl()
         _chk(self.L.iqsb_timer_stop(self.h, ctypes.byref(ms)))
+        return ms.value
+
+    def event_record(self, slot):
+        _chk(self.L.iqsb_event_record(self.h, slot))
+
+    def event_elapsed(self, a, b):
+        ms = c_dbl()
+        _chk(self.L.iqsb_event_elapsed(self.h, a, b, ctypes.byref(ms)))
         return ms.value
 
     def allreduce(self, values, op=SUM):
@@ -331,6 +341,9 @@ class State:
     def gate1_global(self, M, pos, m):
         mm = _m(m)
         _chk(self.L.iqsb_gate1_global(self.h, M, pos, mm.ctypes.data_as(c_vp)))
+
+    def idle_global(self):
+        _chk(self.L.iqsb_idle_global(self.h))
 
     def cgate1_global(self, M, cpos, tpos, m):
         mm = _m(m)

@@ -84,6 +84,11 @@ extern "C" int iqsb_finalize(iqsb_ctx *ctx) {
   cudaFree(ctx->d_result);
   cudaFree(ctx->d_flags);
   cudaFreeHost(ctx->h_result);
+  if (ctx->slots) {
+    for (int i = 0; i < kMaxEventSlots; ++i)
+      if (ctx->slots[i]) cudaEventDestroy(ctx->slots[i]);
+    delete[] ctx->slots;
+  }
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->own_stream);
@@ -122,6 +127,27 @@ extern "C" int iqsb_timer_stop(iqsb_ctx *ctx, double *elapsed_ms) {
   IQSB_CUDA(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f;
   IQSB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *elapsed_ms = (double)ms;
+  return IQSB_OK;
+}
+
+extern "C" int iqsb_event_record(iqsb_ctx *ctx, int slot) {
+  IQSB_REQUIRE(ctx && slot >= 0 && slot < kMaxEventSlots, "iqsb_event_record: bad slot");
+  if (!ctx->slots) {
+    ctx->slots = new cudaEvent_t[kMaxEventSlots];
+    for (int i = 0; i < kMaxEventSlots; ++i) ctx->slots[i] = nullptr;
+  }
+  if (!ctx->slots[slot]) IQSB_CUDA(cudaEventCreate(&ctx->slots[slot]));
+  IQSB_CUDA(cudaEventRecord(ctx->slots[slot], ctx->stream));
+  return IQSB_OK;
+}
+extern "C" int iqsb_event_elapsed(iqsb_ctx *ctx, int slot_from, int slot_to, double *elapsed_ms) {
+  IQSB_REQUIRE(ctx && elapsed_ms && ctx->slots && slot_from >= 0 && slot_from < kMaxEventSlots && slot_to >= 0 && slot_to < kMaxEventSlots &&
+                   ctx->slots[slot_from] && ctx->slots[slot_to],
+               "iqsb_event_elapsed: slots were not recorded");
+  IQSB_CUDA(cudaEventSynchronize(ctx->slots[slot_to]));
+  float ms = 0.f;
+  IQSB_CUDA(cudaEventElapsedTime(&ms, ctx->slots[slot_from], ctx->slots[slot_to]));
   *elapsed_ms = (double)ms;
   return IQSB_OK;
 }

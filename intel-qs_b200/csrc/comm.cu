@@ -278,6 +278,14 @@ extern "C" int iqsb_gate1_global(iqsb_state *st, unsigned M, unsigned pos, const
   return peer_barrier(ctx);
 }
 
+extern "C" int iqsb_idle_global(iqsb_state *st) {
+  IQSB_REQUIRE(st, "iqsb_idle_global: null argument");
+  iqsb_ctx *ctx = st->ctx;
+  IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_idle_global: register is not shared across ranks");
+  IQSB_TRY(peer_barrier(ctx));
+  return peer_barrier(ctx);
+}
+
 extern "C" int iqsb_cgate1_global(iqsb_state *st, unsigned M, unsigned cpos, unsigned tpos, const double m[8]) {
   IQSB_REQUIRE(st && m, "iqsb_cgate1_global: null argument");
   iqsb_ctx *ctx = st->ctx;

@@ -51,6 +51,7 @@ struct iqsb_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;  // stream in use (own or adopted)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t *slots = nullptr;  // numbered events (iqsb_event_record)
   uint64_t launches = 0;
   uint64_t nvlink_bytes = 0;
   // reduction scratch: per-block partials + final results (device), pinned host mirror
@@ -76,6 +77,7 @@ struct iqsb_state {
 
 constexpr int kMaxRedBlocks = 148 * 8;
 constexpr int kMaxRedOut = 12;
+constexpr int kMaxEventSlots = 4096;
 
 // ---------------------------------------------------------------------------------------
 // device helpers

@@ -1,0 +1,241 @@
+// env.cpp -- iqs::mpi::Environment over the C ABI context (replaces reference src/mpi_env.cpp, the
+// MPI bootstrap, by an NCCL bootstrap: see include/mpi_env.hpp), plus the small free functions of
+// utils.cpp / gate_spec.cpp.
+#include <sys/time.h>
+
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <thread>
+
+#include "../include/bitops.hpp"
+#include "../include/conversion.hpp"
+#include "../include/gate_spec.hpp"
+#include "../include/mpi_env.hpp"
+#include "../include/mpi_utils.hpp"
+#include "../include/utils.hpp"
+#include "iqsb.h"
+
+namespace iqs {
+
+double time_in_seconds(void) {
+  struct timeval tv;
+  gettimeofday(&tv, NULL);
+  return (double)tv.tv_sec + (double)tv.tv_usec / 1000000.0;
+}
+
+void WhatCompileDefinitions() {
+  std::cout << "Compiler flags:\n"
+            << "          INTELQS_HAS_MPI --> [ NO]  (ranks are NCCL peers over NVLink)\n"
+            << "                  USE_MKL --> [ NO]\n"
+            << "                  _OPENMP --> [ NO]  (state loops are CUDA kernels, sm_100a)\n"
+            << "            USE_MM_MALLOC --> [ NO]  (state lives in HBM)\n"
+#ifdef NDEBUG
+            << "                   NDEBUG --> [YES]\n";
+#else
+            << "                   NDEBUG --> [ NO]\n";
+#endif
+}
+
+GateSpec1Q ConvertSpec2to1(GateSpec2Q spec) {
+  switch (spec) {
+    case GateSpec2Q::CHadamard: return GateSpec1Q::Hadamard;
+    case GateSpec2Q::CRotationX: return GateSpec1Q::RotationX;
+    case GateSpec2Q::CRotationY: return GateSpec1Q::RotationY;
+    case GateSpec2Q::CRotationZ: return GateSpec1Q::RotationZ;
+    case GateSpec2Q::CPauliX: return GateSpec1Q::PauliX;
+    case GateSpec2Q::CPauliY: return GateSpec1Q::PauliY;
+    case GateSpec2Q::CPauliZ: return GateSpec1Q::PauliZ;
+    default: return GateSpec1Q::None;
+  }
+}
+
+namespace mpi {
+
+Environment *Environment::shared_instance = nullptr;
+bool Environment::useful_rank = true;
+bool Environment::is_verbose = true;
+
+namespace {
+iqsb_ctx *g_ctx = nullptr;
+int g_rank = 0, g_size = 1;
+bool g_finalized = false;
+
+[[noreturn]] void die(const char *what) {
+  fprintf(stderr, "iqs (B200 engine): %s: %s\n", what, iqsb_last_error());
+  throw std::runtime_error(std::string(what) + ": " + iqsb_last_error());
+}
+
+const char *env_first(const char *a, const char *b) {
+  const char *v = getenv(a);
+  if (v && *v) return v;
+  v = getenv(b);
+  return (v && *v) ? v : nullptr;
+}
+
+void create_context(int rank, int nranks, const void *uid, int device) {
+  if (g_ctx) return;
+  if (iqsb_init(rank, nranks, uid, device, &g_ctx) != IQSB_OK) die("cannot create the engine context");
+  g_rank = rank;
+  g_size = nranks;
+}
+}  // namespace
+
+void Environment::Bootstrap() {
+  if (g_ctx) return;
+  const char *r = env_first("IQS_RANK", "RANK"), *s = env_first("IQS_NRANKS", "WORLD_SIZE");
+  int rank = r ? atoi(r) : 0, world = s ? atoi(s) : 1;
+  if (world <= 1) {
+    create_context(0, 1, nullptr, -1);
+    return;
+  }
+  // state ranks must be a power of two: the surplus ranks are "dummy" (reference mpi_env.cpp:239-300)
+  int used = (int)floor_power_of_two(world);
+  if (rank >= used) {
+    useful_rank = false;
+    return;
+  }
+  const char *lr = env_first("IQS_LOCAL_RANK", "LOCAL_RANK");
+  int device = lr ? atoi(lr) : -1;
+  std::string file;
+  if (const char *f = getenv("IQS_UID_FILE")) file = f;
+  else {
+    const char *port = getenv("MASTER_PORT");
+    file = std::string("/dev/shm/iqs_b200_uid_") + (port ? std::string(port) : toString((long)getppid()));
+  }
+  unsigned char uid[IQSB_UNIQUE_ID_BYTES];
+  if (rank == 0) {
+    if (iqsb_unique_id(uid) != IQSB_OK) die("cannot create the NCCL unique id");
+    std::string tmp = file + ".tmp";
+    FILE *fp = fopen(tmp.c_str(), "wb");
+    if (!fp || fwrite(uid, 1, sizeof(uid), fp) != sizeof(uid)) throw std::runtime_error("cannot write " + tmp);
+    fclose(fp);
+    rename(tmp.c_str(), file.c_str());
+  } else {
+    FILE *fp = nullptr;
+    for (int tries = 0; tries < 6000 && !(fp = fopen(file.c_str(), "rb")); ++tries) std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    if (!fp || fread(uid, 1, sizeof(uid), fp) != sizeof(uid)) throw std::runtime_error("cannot read the NCCL id from " + file);
+    fclose(fp);
+  }
+  create_context(rank, used, uid, device);
+  if (rank == 0 && !getenv("IQS_UID_FILE")) {
+    iqsb_barrier(g_ctx);  // everybody is connected: the rendezvous file is no longer needed
+    remove(file.c_str());
+  } else if (!getenv("IQS_UID_FILE")) {
+    iqsb_barrier(g_ctx);
+  }
+}
+
+iqsb_ctx *Environment::Context() {
+  if (!g_ctx) {
+    if (g_finalized) throw std::runtime_error("iqs: the environment was finalized");
+    Bootstrap();
+    if (!g_ctx) throw std::runtime_error("iqs: this is a dummy rank (IsUsefulRank() == false); it must not touch registers");
+  }
+  return g_ctx;
+}
+
+void Environment::InitWithUniqueId(int rank, int nranks, const void *uid128, int device) {
+  if (g_ctx) return;
+  create_context(rank, nranks, uid128, device);
+}
+void Environment::GetUniqueId(void *out128) {
+  if (iqsb_unique_id(out128) != IQSB_OK) die("cannot create the NCCL unique id");
+}
+
+Environment::Environment(int &, char **&, bool verbose) : inited_(true) {
+  is_verbose = verbose;
+  Bootstrap();
+  shared_instance = this;
+}
+Environment::Environment() : inited_(true) {
+  Bootstrap();
+  shared_instance = this;
+}
+Environment::~Environment() {
+  if (shared_instance == this) shared_instance = nullptr;
+}
+
+void Environment::Init() {
+  if (shared_instance != nullptr) throw std::runtime_error("iqs::mpi::Environment::Init: environment already initialized");
+  shared_instance = new Environment();
+}
+void Environment::Init(int &argc, char **&argv) {
+  if (shared_instance != nullptr) throw std::runtime_error("iqs::mpi::Environment::Init: environment already initialized");
+  shared_instance = new Environment(argc, argv);
+}
+void Environment::Finalize() {
+  if (shared_instance) {
+    delete shared_instance;
+    shared_instance = nullptr;
+  }
+  if (g_ctx) {
+    iqsb_finalize(g_ctx);
+    g_ctx = nullptr;
+    g_finalized = false;  // a later Init() may start a new context
+  }
+}
+
+void Environment::UpdateStateComm(int new_num_states) {
+  if (new_num_states != 1)
+    throw std::runtime_error("iqs::mpi::Environment::UpdateStateComm: pools of several states run as independent replicas on this engine (num_states must be 1)");
+}
+
+int Environment::GetPoolRank() { return g_rank; }
+int Environment::GetStateRank() { return g_rank; }
+int Environment::GetPoolSize() { return g_size; }
+int Environment::GetStateSize() { return g_size; }
+int Environment::GetNumRanksPerNode() { return g_size; }
+int Environment::GetNumNodes() { return 1; }
+int Environment::GetNodeId() { return 0; }
+int Environment::GetStateId() { return 0; }
+int Environment::GetNumStates() { return 1; }
+// The reference renumbers ranks to implement X/Y on a global qubit without data movement
+// (spec-v1 only, flagged buggy: qureg_apply1qubitgate.cpp:61-99).  Not used by this engine.
+void Environment::RemapStateRank(int) {}
+
+template <class Type>
+Type Environment::IncoherentSumOverAllStatesOfPool(Type local_value) {
+  return local_value;  // one state in the pool
+}
+template float Environment::IncoherentSumOverAllStatesOfPool<float>(float);
+template double Environment::IncoherentSumOverAllStatesOfPool<double>(double);
+
+// Barriers also drain the engine's stream: after StateBarrier() the host may read managed state.
+void StateBarrier() {
+  if (g_ctx && iqsb_barrier(g_ctx) != IQSB_OK) die("barrier failed");
+}
+void PoolBarrier() { StateBarrier(); }
+void Barrier() { StateBarrier(); }
+
+void StatePrint(std::string s, bool all) {
+  int rank = Environment::GetStateRank(), size = Environment::GetStateSize();
+  if (all) {
+    for (int r = 0; r < size; ++r) {
+      if (r == rank) {
+        printf("[|%d>:%3d] %s\n", Environment::GetStateId(), rank, s.c_str());
+        fflush(stdout);
+      }
+      StateBarrier();
+    }
+  } else if (rank == 0) {
+    std::cout << s << std::endl;
+  }
+}
+void PoolPrint(std::string s, bool all) { StatePrint(s, all); }
+void Print(std::string s, bool all) { StatePrint(s, all); }
+
+void AllreduceDouble(double *inout, int n, ReduceOp op) {
+  if (g_size == 1) return;
+  if (iqsb_allreduce_f64(Environment::Context(), inout, n, op == MAX ? IQSB_MAX : IQSB_SUM) != IQSB_OK) die("allreduce failed");
+}
+void BcastDouble(double *inout, int n, int root) {
+  if (g_size == 1) return;
+  if (iqsb_bcast_f64(Environment::Context(), inout, n, root) != IQSB_OK) die("broadcast failed");
+}
+
+}  // namespace mpi
+}  // namespace iqs

@@ -1,0 +1,187 @@
+// qureg_measure.cpp -- probabilities, collapse, classical-bit tests and expectation values.
+//
+// Reference behaviour restated: src/qureg_measure.cpp (IsClassicalBit :19-81, CollapseQubit :92-126,
+// GetProbability :135-178, GetClassicalValue :183-262) and src/qureg_expectval.cpp (:18-375).
+// The serial CPU sums become warp-shuffle reductions (csrc/kernels_reduce.cu) followed by an NCCL
+// all-reduce of one double when the register spans several ranks.
+#include "qureg_impl.hpp"
+
+namespace iqs {
+
+using detail::Check;
+
+template <class Type>
+bool QubitRegister<Type>::IsClassicalBit(unsigned qubit, BaseType tolerance) const {
+  assert(qubit < num_qubits);
+  unsigned position = (*qubit_permutation)[qubit];
+  assert(position < num_qubits);
+  const_cast<QubitRegister *>(this)->FlushForRead();
+  BeforeDeviceOp();
+  std::size_t glb_start = UL(iqs::mpi::Environment::GetStateRank()) * LocalSize();
+  int flags[2] = {0, 0};
+  Check(iqsb_any_above(dev_, position, (double)tolerance, glb_start, flags), "IsClassicalBit");
+  double v[2] = {double(flags[0]), double(flags[1])};
+  iqs::mpi::AllreduceDouble(v, 2, iqs::mpi::MAX);  // logical OR over the ranks (measure.cpp:69-70)
+  return !(v[0] > 0 && v[1] > 0);
+}
+
+template <class Type>
+void QubitRegister<Type>::CollapseQubit(unsigned qubit, bool value) {
+  assert(qubit < num_qubits);
+  unsigned position = (*qubit_permutation)[qubit];
+  assert(position < num_qubits);
+  FlushForRead();
+  BeforeDeviceOp();
+  unsigned M = LocalQubits();
+  if (position < M) {
+    Check(iqsb_collapse(dev_, position, value ? 1 : 0), "CollapseQubit");
+  } else {
+    std::size_t glb_start = UL(iqs::mpi::Environment::GetStateRank()) * LocalSize();
+    if (check_bit(glb_start, position) != value) Check(iqsb_fill_const(dev_, 0., 0.), "CollapseQubit");
+  }
+}
+
+template <class Type>
+typename QubitRegister<Type>::BaseType QubitRegister<Type>::GetProbability(unsigned qubit) {
+  assert(qubit < num_qubits);
+  unsigned position = (*qubit_permutation)[qubit];
+  assert(position < num_qubits);
+  FlushForRead();
+  BeforeDeviceOp();
+  unsigned M = LocalQubits();
+  double p = 0.;
+  if (position < M) {
+    Check(iqsb_prob1(dev_, position, &p), "GetProbability");
+  } else {
+    std::size_t glb_start = UL(iqs::mpi::Environment::GetStateRank()) * LocalSize();
+    if (check_bit(glb_start, position) == 1) Check(iqsb_norm2(dev_, &p), "GetProbability");
+  }
+  iqs::mpi::AllreduceDouble(&p, 1, iqs::mpi::SUM);
+  return (BaseType)p;
+}
+
+template <class Type>
+bool QubitRegister<Type>::GetClassicalValue(unsigned qubit, BaseType tolerance) const {
+  assert(qubit < num_qubits);
+  unsigned position = (*qubit_permutation)[qubit];
+  assert(position < num_qubits);
+  const_cast<QubitRegister *>(this)->FlushForRead();
+  BeforeDeviceOp();
+  std::size_t glb_start = UL(iqs::mpi::Environment::GetStateRank()) * LocalSize();
+  int flags[2] = {0, 0};
+  Check(iqsb_any_above(dev_, position, (double)tolerance, glb_start, flags), "GetClassicalValue");
+  double v[2] = {double(flags[0]), double(flags[1])};
+  iqs::mpi::AllreduceDouble(v, 2, iqs::mpi::MAX);
+  bool zero = v[0] > 0, one = v[1] > 0;
+  if (zero && !one) return false;
+  if (!zero && one) return true;
+  assert(false && "GetClassicalValue: the qubit is not in a classical state");
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// expectation values
+// ---------------------------------------------------------------------------------------------
+template <class Type>
+typename QubitRegister<Type>::BaseType QubitRegister<Type>::ExpectationValueX(unsigned qubit, BaseType coeff) {
+  // <X> = <psi| H.Z.H |psi>
+  ApplyHadamard(qubit);
+  BaseType expectation = 1. - 2. * GetProbability(qubit);
+  ApplyHadamard(qubit);
+  return coeff * expectation;
+}
+
+template <class Type>
+typename QubitRegister<Type>::BaseType QubitRegister<Type>::ExpectationValueY(unsigned qubit, BaseType coeff) {
+  // G^dagger.Z.G = Y
+  TM2x2<Type> G;
+  BaseType f = 1. / std::sqrt(2.);
+  G(0, 0) = G(1, 0) = Type(f, 0.);
+  G(0, 1) = Type(0., -f);
+  G(1, 1) = Type(0., f);
+  Apply1QubitGate(qubit, G);
+  BaseType expectation = 1. - 2. * GetProbability(qubit);
+  G(0, 0) = G(0, 1) = Type(f, 0.);
+  G(1, 0) = Type(0., f);
+  G(1, 1) = Type(0., -f);
+  Apply1QubitGate(qubit, G);
+  return coeff * expectation;
+}
+
+template <class Type>
+typename QubitRegister<Type>::BaseType QubitRegister<Type>::ExpectationValueZ(unsigned qubit, BaseType coeff) {
+  BaseType expectation = 1. - 2. * GetProbability(qubit);
+  return coeff * expectation;
+}
+
+// observable: 1 == PauliX, 2 == PauliY, 3 == PauliZ
+template <class Type>
+typename QubitRegister<Type>::BaseType QubitRegister<Type>::ExpectationValue(std::vector<unsigned> &qubits,
+                                                                            std::vector<unsigned> &observables, BaseType coeff) {
+  assert(qubits.size() == observables.size());
+  for (unsigned j = 0; j < qubits.size(); ++j) {
+    assert(qubits[j] < num_qubits);
+    assert(observables[j] > 0 && observables[j] < 4);
+  }
+  if (qubits.size() == 0) return coeff;
+  if (qubits.size() == 1) {
+    if (observables[0] == 1) return ExpectationValueX(qubits[0], coeff);
+    if (observables[0] == 2) return ExpectationValueY(qubits[0], coeff);
+    if (observables[0] == 3) return ExpectationValueZ(qubits[0], coeff);
+  }
+  TM2x2<Type> G, Ginv;
+  BaseType f = 1. / std::sqrt(2.);
+  G(0, 0) = G(1, 0) = Type(f, 0.);
+  G(0, 1) = Type(0., -f);
+  G(1, 1) = Type(0., f);
+  Ginv(0, 0) = Ginv(0, 1) = Type(f, 0.);
+  Ginv(1, 0) = Type(0., f);
+  Ginv(1, 1) = Type(0., -f);
+
+  for (std::size_t i = 0; i < qubits.size(); i++) {
+    if (observables[i] == 1) ApplyHadamard(qubits[i]);
+    else if (observables[i] == 2) Apply1QubitGate(qubits[i], G);
+  }
+
+  // signed sum of |a|^2, sign = parity of the involved bits of the GLOBAL index.  The mask is
+  // built with 64-bit shifts (the reference's `1 << position` overflows at position 31, :170).
+  std::size_t myrank = iqs::mpi::Environment::GetStateRank();
+  std::size_t glb_start = UL(myrank) * LocalSize();
+  std::size_t y = 0;
+  for (std::size_t i = 0; i < qubits.size(); i++) y += std::size_t(1) << (*qubit_permutation)[qubits[i]];
+  FlushForRead();
+  BeforeDeviceOp();
+  double v = 0;
+  Check(iqsb_parity_expect(dev_, y, glb_start, &v), "ExpectationValue");
+  iqs::mpi::AllreduceDouble(&v, 1, iqs::mpi::SUM);
+  BaseType expectation = (BaseType)v;
+
+  for (std::size_t i = 0; i < qubits.size(); i++) {
+    if (observables[i] == 1) ApplyHadamard(qubits[i]);
+    else if (observables[i] == 2) Apply1QubitGate(qubits[i], Ginv);
+  }
+  return coeff * expectation;
+}
+
+#define IQS_EXPECT2(NAME, O1, O2)                                                                                   \
+  template <class Type>                                                                                             \
+  typename QubitRegister<Type>::BaseType QubitRegister<Type>::NAME(unsigned qubit, unsigned qubit2, BaseType coeff) { \
+    std::vector<unsigned> qubits = {qubit, qubit2};                                                                 \
+    std::vector<unsigned> observables = {O1, O2};                                                                   \
+    return this->ExpectationValue(qubits, observables, coeff);                                                      \
+  }
+IQS_EXPECT2(ExpectationValueXX, 1, 1)
+IQS_EXPECT2(ExpectationValueXY, 1, 2)
+IQS_EXPECT2(ExpectationValueXZ, 1, 3)
+IQS_EXPECT2(ExpectationValueYX, 2, 1)
+IQS_EXPECT2(ExpectationValueYY, 2, 2)
+IQS_EXPECT2(ExpectationValueYZ, 2, 3)
+IQS_EXPECT2(ExpectationValueZX, 3, 1)
+IQS_EXPECT2(ExpectationValueZY, 3, 2)
+IQS_EXPECT2(ExpectationValueZZ, 3, 3)
+#undef IQS_EXPECT2
+
+template class QubitRegister<ComplexSP>;
+template class QubitRegister<ComplexDP>;
+
+}  // namespace iqs

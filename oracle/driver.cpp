@@ -8,7 +8,7 @@
 //       -> intel-qs_b200/bin/iqs_b200_driver (the drop-in proof: no source change)
 //
 // usage: driver <program.bin> [--state-in s.bin] [--state-out s.bin] [--scalars-out x.bin]
-//               [--map-out m.bin] [--repeat R] [--quiet]
+//               [--map-out m.bin] [--repeat R] [--step-sizes a,b,c]
 // Prints one line "TIME <seconds> OPS <count>" for the timed replay (init excluded).
 #include <chrono>
 #include <cstdio>
@@ -134,6 +134,7 @@ int main(int argc, char **argv) {
   }
   const char *state_in = nullptr, *state_out = nullptr, *scalars_out = nullptr, *map_out = nullptr;
   int repeat = 1;
+  std::vector<std::size_t> step_sizes;
   for (int i = 2; i < argc; ++i) {
     std::string a = argv[i];
     if (a == "--state-in" && i + 1 < argc) state_in = argv[++i];
@@ -141,6 +142,15 @@ int main(int argc, char **argv) {
     else if (a == "--scalars-out" && i + 1 < argc) scalars_out = argv[++i];
     else if (a == "--map-out" && i + 1 < argc) map_out = argv[++i];
     else if (a == "--repeat" && i + 1 < argc) repeat = atoi(argv[++i]);
+    else if (a == "--step-sizes" && i + 1 < argc) {  // comma separated op counts, one per timed step
+      std::string list = argv[++i];
+      for (std::size_t p = 0; p < list.size();) {
+        std::size_t q = list.find(',', p);
+        if (q == std::string::npos) q = list.size();
+        step_sizes.push_back((std::size_t)atol(list.substr(p, q - p).c_str()));
+        p = q + 1;
+      }
+    }
   }
   FILE *f = fopen(argv[1], "rb");
   if (!f) { perror("program"); return 1; }
@@ -173,9 +183,24 @@ int main(int argc, char **argv) {
   std::vector<double> scalars;
   psi.ComputeNorm();  // settle the state in its home memory before the clock starts
   auto t0 = std::chrono::steady_clock::now();
-  for (int r = 0; r < repeat; ++r) {
-    if (r) scalars.clear();
-    run_ops(psi, ops, scalars);
+  if (!step_sizes.empty()) {
+    // timed step by step: one "STEP i seconds" line each (ComputeNorm closes a step so that
+    // asynchronous engines have finished it)
+    for (std::size_t first = 0, s = 0; first < ops.size() && s < step_sizes.size(); first += step_sizes[s], ++s) {
+      std::size_t last = std::min(ops.size(), first + step_sizes[s]);
+      std::vector<iqs_op> part(ops.begin() + first, ops.begin() + last);
+      auto s0 = std::chrono::steady_clock::now();
+      run_ops(psi, part, scalars);
+      psi.ComputeNorm();
+      auto s1 = std::chrono::steady_clock::now();
+      if (iqs::mpi::Environment::GetStateRank() == 0)
+        printf("STEP %zu %.6f\n", s, std::chrono::duration<double>(s1 - s0).count());
+    }
+  } else {
+    for (int r = 0; r < repeat; ++r) {
+      if (r) scalars.clear();
+      run_ops(psi, ops, scalars);
+    }
   }
   double nrm = psi.ComputeNorm();  // forces completion of asynchronous engines
   auto t1 = std::chrono::steady_clock::now();

@@ -176,7 +176,7 @@ def have_ref_driver():
     return os.path.exists(REF_DRIVER)
 
 
-def run_driver(driver, program, state=None, init=1, base_index=0, threads=None, repeat=1, want_state=True, extra_env=None):
+def run_driver(driver, program, state=None, init=1, base_index=0, threads=None, repeat=1, want_state=True, extra_env=None, launcher=None):
     """Run a driver binary (reference or drop-in) on `program`.
     Returns dict(state, scalars, map, seconds)."""
     n = program.n
@@ -191,7 +191,7 @@ def run_driver(driver, program, state=None, init=1, base_index=0, threads=None, 
             init = 0
             np.ascontiguousarray(state, dtype=np.complex128).tofile(os.path.join(td, "in.bin"))
         program.write(pf, init=init, base_index=base_index)
-        cmd = [driver, pf, "--scalars-out", os.path.join(td, "scal.bin"), "--map-out", os.path.join(td, "map.bin"), "--repeat", str(repeat)]
+        cmd = list(launcher or []) + [driver, pf, "--scalars-out", os.path.join(td, "scal.bin"), "--map-out", os.path.join(td, "map.bin"), "--repeat", str(repeat)]
         if state is not None:
             cmd += ["--state-in", os.path.join(td, "in.bin")]
         if want_state:

@@ -1,0 +1,113 @@
+"""Distributed parity on 2/4/8 GPUs of one box (skipped when fewer are visible): the drop-in driver
+is launched with tools/iqsrun (one process per GPU, NCCL bootstrap, cudaIpc peer memory); the global
+state gathered from the shards must equal the single-rank oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from pkg import circuits as C
+from progs import random_program
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "intel-qs_b200", "bin", "iqs_b200_driver")
+IQSRUN = os.path.join(ROOT, "tools", "iqsrun")
+TOL = 1e-12
+
+
+def gpu_count():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        return sum(1 for l in out.splitlines() if l.startswith("GPU "))
+    except Exception:
+        return 0
+
+
+NGPU = gpu_count()
+
+
+def run_ranks(oracle, nranks, prog, state=None, **kw):
+    launcher = [sys.executable, IQSRUN, "-n", str(nranks), "--timeout", "300"]
+    return oracle.run_driver(DRIVER, prog, state=state, launcher=launcher, **kw)
+
+
+def need(n):
+    if NGPU < n:
+        pytest.skip(f"needs {n} GPUs, {NGPU} visible")
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+@pytest.mark.parametrize("n,seed", [(8, 1), (12, 2)])
+def test_random_programs_sharded(oracle, nranks, n, seed):
+    need(nranks)
+    prog = random_program(n, 250, seed, toffoli=True)
+    psi = C.random_state(n, seed)
+    want, _, wmap = oracle.run_program(n, psi, prog.ops)
+    got = run_ranks(oracle, nranks, prog, state=psi)
+    assert np.array_equal(got["map"], wmap)
+    err = np.max(np.abs(got["state"] - want))
+    assert err <= TOL, f"{nranks} ranks: max |amp - oracle| = {err}"
+    assert np.array_equal(got["state"], want)
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_scalars_and_measurement_sharded(oracle, nranks):
+    need(nranks)
+    n, seed = 10, 4
+    prog = random_program(n, 120, seed)
+    for q in range(n):
+        prog.prob(q)
+    prog.expect([0, n - 1], [1, 3]).expect([n - 1, n - 2, 1], [2, 1, 3]).expect1(n - 1, 1).expect1(n - 1, 2).expect1(0, 3).norm()
+    prog.collapse(n - 1, 1).normalize().norm().collapse(0, 0).normalize().prob(n - 1)
+    psi = C.random_state(n, seed)
+    want, wsc, _ = oracle.run_program(n, psi, prog.ops)
+    got = run_ranks(oracle, nranks, prog, state=psi)
+    assert np.max(np.abs(got["scalars"] - wsc)) <= TOL
+    assert np.max(np.abs(got["state"] - want)) <= TOL
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_permute_qubits_sharded_bit_exact(oracle, nranks):
+    """qureg_permute_test.hpp: local, global and mixed permutations move amplitudes exactly."""
+    need(nranks)
+    n = 10
+    rng = np.random.default_rng(nranks)
+    psi = (np.arange(1 << n) + 1j * (np.arange(1 << n) + 0.25)).astype(np.complex128)
+    prog = C.Program(n)
+    prog.permute(list(rng.permutation(n)))
+    prog.permute(list(range(n))[::-1])
+    prog.named1(C.H, 0).named2(C.CX, 0, n - 1)
+    prog.permute(list(rng.permutation(n)))
+    want, _, wmap = oracle.run_program(n, psi, prog.ops)
+    got = run_ranks(oracle, nranks, prog, state=psi)
+    assert np.array_equal(got["map"], wmap)
+    assert np.array_equal(got["state"], want)
+
+
+@pytest.mark.parametrize("nranks", [2, 8])
+def test_qft_sharded(oracle, nranks):
+    """BASELINE configs[2] at a size the oracle finishes in seconds."""
+    need(nranks)
+    n = 16
+    prog = C.qft(n)
+    psi = C.random_state(n, seed=777)
+    want, _, _ = oracle.run_program(n, psi, prog.ops)
+    got = run_ranks(oracle, nranks, prog, state=psi)
+    assert np.max(np.abs(got["state"] - want)) <= TOL
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_fusion_sharded(oracle, nranks):
+    need(nranks)
+    n = 13
+    prog = C.Program(n).mode(C.FUSION_ON, 8)
+    prog.extend(random_program(n, 200, 5, kinds="basic"))
+    prog.mode(C.FUSION_OFF)
+    psi = C.random_state(n, 6)
+    want, _, _ = oracle.run_program(n, psi, prog.ops)
+    got = run_ranks(oracle, nranks, prog, state=psi)
+    assert np.array_equal(got["state"], want)

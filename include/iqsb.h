@@ -176,6 +176,23 @@ int iqsb_axpy(iqsb_state *a, const iqsb_state *b, const double f[2]);
 int iqsb_permute_local(iqsb_state *st, const uint8_t *dst_bit, unsigned nbits);
 
 /* ---- distributed (nranks > 1): fused compute + NVLink peer access -------------------- */
+/* Pure host function (no GPU needed): which pairs of a gate on a global qubit THIS rank updates.
+ * The rank updates the pairs (s0[k + extra0], s1[k + extra1]) for every local index k whose bits
+ * pos[i] equal val[i] (i < nfix); s0 is the shard of the rank on the "0 side" of the pair, s1 the
+ * other; role says which of the two is this rank's own shard (0: s0 is mine, 1: s1 is mine).
+ * kind 0: 1-qubit gate on global pos2; 1: controlled gate, control pos1 local, target pos2 global;
+ * 2: swap-family gate on pos1 < pos2 with pos2 global. */
+typedef struct iqsb_plan {
+  int32_t active;  /* 0: this rank owns no pair of this gate (it still joins the rendezvous) */
+  int32_t partner; /* rank whose shard is read and written over NVLink */
+  int32_t role;
+  int32_t nfix;
+  uint32_t pos[3], val[3];
+  uint64_t extra0, extra1;
+  uint64_t npairs;
+  uint64_t link_amps; /* amplitudes crossing the link per direction (algorithmic) */
+} iqsb_plan;
+int iqsb_plan_global(int kind, int rank, int nranks, unsigned M, unsigned pos1, unsigned pos2, iqsb_plan *out);
 /* publish the shard to the peers (cudaIpc) -- collective over all ranks of the context. */
 int iqsb_share(iqsb_state *st);
 /* 1-qubit gate on global position pos >= M: replaces HP_Distrpair(P) (src/qureg_apply1qubitgate.cpp:18-169) */

@@ -24,6 +24,19 @@ class IqsbError(RuntimeError):
     pass
 
 
+class Plan(ctypes.Structure):
+    _fields_ = [("active", ctypes.c_int32), ("partner", ctypes.c_int32), ("role", ctypes.c_int32), ("nfix", ctypes.c_int32),
+                ("pos", ctypes.c_uint32 * 3), ("val", ctypes.c_uint32 * 3), ("extra0", ctypes.c_uint64), ("extra1", ctypes.c_uint64),
+                ("npairs", ctypes.c_uint64), ("link_amps", ctypes.c_uint64)]
+
+
+def plan_global(kind, rank, nranks, M, pos1, pos2):
+    """Host-only: the pairs of a global-qubit gate that `rank` updates (include/iqsb.h, iqsb_plan)."""
+    pl = Plan()
+    _chk(load().iqsb_plan_global(kind, rank, nranks, M, pos1, pos2, ctypes.byref(pl)))
+    return pl
+
+
 class FGate(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("control", ctypes.c_int32), ("target", ctypes.c_int32), ("pad", ctypes.c_int32), ("m", c_dbl * 8)]
 
@@ -87,6 +100,7 @@ def load():
         "iqsb_collapse": [c_vp, c_uint, c_int],
         "iqsb_axpy": [c_vp, c_vp, c_vp],
         "iqsb_permute_local": [c_vp, c_vp, c_uint],
+        "iqsb_plan_global": [c_int, c_int, c_int, c_uint, c_uint, c_uint, c_vp],
         "iqsb_share": [c_vp],
         "iqsb_idle_global": [c_vp],
         "iqsb_gate1_global": [c_vp, c_uint, c_uint, c_vp],
@@ -120,6 +134,10 @@ def _m(m, n=8):
 def _c2(z):
     z = complex(z)
     return np.array([z.real, z.imag], dtype=np.float64)
+
+
+def version():
+    return int(load().iqsb_version())
 
 
 def unique_id():

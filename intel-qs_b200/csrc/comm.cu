@@ -219,63 +219,130 @@ int iqsb_comm_unshare(iqsb_state *st) {
 // ---------------------------------------------------------------------------------------
 // global-qubit gates
 // ---------------------------------------------------------------------------------------
+// Who updates which pairs is decided by a pure host function, iqsb_plan_global, so that the
+// partition logic can be exercised without a GPU (tests/test_partition_gloo.py).
 namespace {
 
-// Launch the two-pointer pair kernel on the subset {k : bits fixed as given} of the local
-// index space; s0/s1 are shard base pointers (possibly remote), off0/off1 extra amplitude
-// offsets added on each side (in amplitudes).
-int launch_split(iqsb_state *st, void *s0, void *s1, int nfix, const unsigned *pos, const unsigned *val,
-                 uint64_t extra0, uint64_t extra1, const double m[8]) {
+// highest local bit that is not in `avoid` (or -1)
+int pick_split_bit(unsigned M, int avoid) {
+  for (int b = (int)M - 1; b >= 0; --b)
+    if (b != avoid) return b;
+  return -1;
+}
+
+void add_fix(iqsb_plan *p, unsigned pos, unsigned val) {
+  p->pos[p->nfix] = pos;
+  p->val[p->nfix] = val;
+  p->nfix++;
+}
+
+// Launch the two-pointer pair kernel for a plan; s0/s1 are shard base pointers (possibly remote).
+int launch_plan(iqsb_state *st, const iqsb_plan &pl, void *s0, void *s1, const double m[8]) {
   unsigned p[3], v[3];
-  for (int i = 0; i < nfix; ++i) { p[i] = pos[i]; v[i] = val[i]; }
+  int nfix = pl.nfix;
+  for (int i = 0; i < nfix; ++i) { p[i] = pl.pos[i]; v[i] = pl.val[i]; }
   for (int i = 0; i < nfix; ++i)
     for (int j = i + 1; j < nfix; ++j)
       if (p[j] < p[i]) { unsigned t = p[i]; p[i] = p[j]; p[j] = t; t = v[i]; v[i] = v[j]; v[j] = t; }
   uint64_t L = st->local_amps;
-  bool w1 = (nfix > 0 && p[0] == 0) || ((extra0 | extra1) & 1) || L < 2;
+  bool w1 = (nfix > 0 && p[0] == 0) || ((pl.extra0 | pl.extra1) & 1) || L < 2;
   unsigned ins[3];
   uint64_t fixed = 0;
   if (w1) {
     for (int i = 0; i < nfix; ++i) { ins[i] = p[i]; fixed |= (uint64_t)v[i] << p[i]; }
-    Geom g = make_geom(L >> nfix, nfix, ins, fixed + extra0, fixed + extra1);
+    Geom g = make_geom(L >> nfix, nfix, ins, fixed + pl.extra0, fixed + pl.extra1);
     return iqsb_launch_pairs(st, s0, s1, 1, g, m);
   }
   for (int i = 0; i < nfix; ++i) { ins[i] = p[i] - 1; fixed |= (uint64_t)v[i] << (p[i] - 1); }
-  Geom g = make_geom((L / 2) >> nfix, nfix, ins, fixed + extra0 / 2, fixed + extra1 / 2);
+  Geom g = make_geom((L / 2) >> nfix, nfix, ins, fixed + pl.extra0 / 2, fixed + pl.extra1 / 2);
   return iqsb_launch_pairs(st, s0, s1, 2, g, m);
 }
 
-// highest local bit that is not in `avoid` (or -1)
-int pick_split_bit(unsigned M, int avoid0, int avoid1) {
-  for (int b = (int)M - 1; b >= 0; --b)
-    if (b != avoid0 && b != avoid1) return b;
-  return -1;
+int run_global(iqsb_state *st, int kind, unsigned M, unsigned pos1, unsigned pos2, const double m[8], const char *what) {
+  iqsb_ctx *ctx = st->ctx;
+  IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "%s: register is not shared across ranks", what);
+  IQSB_REQUIRE(M == st->log2_local, "%s: M must equal log2(local_amps)", what);
+  iqsb_plan pl;
+  IQSB_TRY(iqsb_plan_global(kind, ctx->rank, ctx->nranks, M, pos1, pos2, &pl));
+  IQSB_TRY(peer_barrier(ctx));  // the partner's earlier kernels are complete
+  if (pl.active) {
+    void *mine = st->d, *theirs = st->peer_ptr[pl.partner];
+    IQSB_TRY(launch_plan(st, pl, pl.role == 0 ? mine : theirs, pl.role == 0 ? theirs : mine, m));
+  }
+  ctx->nvlink_bytes += pl.link_amps * st->amp_bytes();
+  return peer_barrier(ctx);  // the partner's stores into this shard are complete
 }
 
 }  // namespace
 
+// kind 0: 1-qubit gate on global position pos2 (pos1 ignored)        -- HP_Distrpair(P)
+// kind 1: controlled gate, control pos1 local, target pos2 global    -- HP_Distrpair(C,T)
+// kind 2: swap-family gate, pos1 < pos2, pos2 global                 -- HP_DistrSwap
+extern "C" int iqsb_plan_global(int kind, int rank, int nranks, unsigned M, unsigned pos1, unsigned pos2, iqsb_plan *out) {
+  IQSB_REQUIRE(out, "iqsb_plan_global: null plan");
+  IQSB_REQUIRE(nranks > 1 && (nranks & (nranks - 1)) == 0 && rank >= 0 && rank < nranks, "iqsb_plan_global: bad rank/nranks");
+  IQSB_REQUIRE(kind >= 0 && kind <= 2, "iqsb_plan_global: bad kind");
+  IQSB_REQUIRE(pos2 >= M && (1u << (pos2 - M)) < (unsigned)nranks, "iqsb_plan_global: position %u is not a global position", pos2);
+  memset(out, 0, sizeof(*out));
+  const uint64_t L = 1ull << M;
+  if (kind == 0 || kind == 1 || (kind == 2 && pos1 < M)) {
+    if (kind == 1) IQSB_REQUIRE(pos1 < M, "iqsb_plan_global: the control must be local");
+    if (kind == 2) IQSB_REQUIRE(pos1 < pos2, "iqsb_plan_global: need pos1 < pos2");
+    // the pair (a on the rank whose pos2 bit is 0, b on its partner) is owned by exactly one of the two
+    // ranks, chosen by one local split bit: bit value 1 -> the 0-side rank (the reference's i-task takes
+    // the upper half, 1q.cpp:130-152), 0 -> the 1-side rank.
+    unsigned rb = pos2 - M;
+    unsigned mybit = (rank >> rb) & 1;
+    out->partner = rank ^ (1 << rb);
+    out->role = (int)mybit;
+    int avoid = kind == 0 ? -1 : (int)pos1;
+    if (kind == 1) add_fix(out, pos1, 1);  // control bit set
+    if (kind == 2) {                       // i0 = base + 2^pos1 on the 0-side, i1 = base on the 1-side
+      add_fix(out, pos1, 0);
+      out->extra0 = 1ull << pos1;
+    }
+    int sb = pick_split_bit(M, avoid);
+    if (sb < 0) out->active = mybit == 0;  // a single pair: the 0-side rank does it
+    else {
+      add_fix(out, (unsigned)sb, mybit ? 0u : 1u);
+      out->active = 1;
+    }
+    out->npairs = out->active ? (L >> out->nfix) : 0;
+    out->link_amps = kind == 0 ? L : L / 2;  // per direction, SURVEY.md 8d
+  } else {
+    // both positions global: ranks with (bit1, bit2) = (1,0) exchange with (0,1); equal bits idle
+    IQSB_REQUIRE(pos1 < pos2, "iqsb_plan_global: need pos1 < pos2");
+    unsigned r1 = pos1 - M, r2 = pos2 - M;
+    unsigned b1 = (rank >> r1) & 1, b2 = (rank >> r2) & 1;
+    if (b1 != b2) {
+      out->partner = rank ^ (1 << r1) ^ (1 << r2);
+      out->role = b1 == 1 ? 0 : 1;  // the rank holding i0 (pos1 bit 1, pos2 bit 0) is the 0-side
+      int sb = pick_split_bit(M, -1);
+      if (sb < 0) out->active = out->role == 0;
+      else {
+        add_fix(out, (unsigned)sb, out->role == 0 ? 1u : 0u);
+        out->active = 1;
+      }
+      out->npairs = out->active ? (L >> out->nfix) : 0;
+      out->link_amps = L;
+    }
+  }
+  return IQSB_OK;
+}
+
 extern "C" int iqsb_gate1_global(iqsb_state *st, unsigned M, unsigned pos, const double m[8]) {
   IQSB_REQUIRE(st && m, "iqsb_gate1_global: null argument");
-  iqsb_ctx *ctx = st->ctx;
-  IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_gate1_global: register is not shared across ranks");
-  IQSB_REQUIRE(M == st->log2_local && pos >= M && (1u << (pos - M)) < (unsigned)ctx->nranks, "iqsb_gate1_global: bad position");
-  unsigned rb = pos - M;
-  int partner = ctx->rank ^ (1 << rb);
-  unsigned mybit = (ctx->rank >> rb) & 1;
-  void *s0 = mybit ? st->peer_ptr[partner] : st->d;  // side whose target bit is 0
-  void *s1 = mybit ? st->d : st->peer_ptr[partner];
-  IQSB_TRY(peer_barrier(ctx));
-  int sb = pick_split_bit(M, -1, -1);
-  int rc;
-  if (sb < 0) {  // one amplitude per rank: the bit-0 rank does the single pair
-    rc = mybit ? IQSB_OK : launch_split(st, s0, s1, 0, nullptr, nullptr, 0, 0, m);
-  } else {
-    unsigned p[1] = {(unsigned)sb}, v[1] = {mybit ? 0u : 1u};  // i-task takes the upper half (reference 1q.cpp:130-152)
-    rc = launch_split(st, s0, s1, 1, p, v, 0, 0, m);
-  }
-  IQSB_TRY(rc);
-  ctx->nvlink_bytes += st->local_amps * st->amp_bytes();
-  return peer_barrier(ctx);
+  return run_global(st, 0, M, 0, pos, m, "iqsb_gate1_global");
+}
+
+extern "C" int iqsb_cgate1_global(iqsb_state *st, unsigned M, unsigned cpos, unsigned tpos, const double m[8]) {
+  IQSB_REQUIRE(st && m, "iqsb_cgate1_global: null argument");
+  return run_global(st, 1, M, cpos, tpos, m, "iqsb_cgate1_global");
+}
+
+extern "C" int iqsb_swap2x2_global(iqsb_state *st, unsigned M, unsigned pos1, unsigned pos2, const double m[8]) {
+  IQSB_REQUIRE(st && m, "iqsb_swap2x2_global: null argument");
+  return run_global(st, 2, M, pos1, pos2, m, "iqsb_swap2x2_global");
 }
 
 extern "C" int iqsb_idle_global(iqsb_state *st) {
@@ -283,79 +350,6 @@ extern "C" int iqsb_idle_global(iqsb_state *st) {
   iqsb_ctx *ctx = st->ctx;
   IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_idle_global: register is not shared across ranks");
   IQSB_TRY(peer_barrier(ctx));
-  return peer_barrier(ctx);
-}
-
-extern "C" int iqsb_cgate1_global(iqsb_state *st, unsigned M, unsigned cpos, unsigned tpos, const double m[8]) {
-  IQSB_REQUIRE(st && m, "iqsb_cgate1_global: null argument");
-  iqsb_ctx *ctx = st->ctx;
-  IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_cgate1_global: register is not shared across ranks");
-  IQSB_REQUIRE(M == st->log2_local && cpos < M && tpos >= M && (1u << (tpos - M)) < (unsigned)ctx->nranks,
-               "iqsb_cgate1_global: need control local and target global");
-  unsigned rb = tpos - M;
-  int partner = ctx->rank ^ (1 << rb);
-  unsigned mybit = (ctx->rank >> rb) & 1;
-  void *s0 = mybit ? st->peer_ptr[partner] : st->d;
-  void *s1 = mybit ? st->d : st->peer_ptr[partner];
-  IQSB_TRY(peer_barrier(ctx));
-  int sb = pick_split_bit(M, (int)cpos, -1);
-  int rc;
-  if (sb < 0) {
-    unsigned p[1] = {cpos}, v[1] = {1};
-    rc = mybit ? IQSB_OK : launch_split(st, s0, s1, 1, p, v, 0, 0, m);
-  } else {
-    unsigned p[2] = {cpos, (unsigned)sb}, v[2] = {1, mybit ? 0u : 1u};
-    rc = launch_split(st, s0, s1, 2, p, v, 0, 0, m);
-  }
-  IQSB_TRY(rc);
-  ctx->nvlink_bytes += st->local_amps / 2 * st->amp_bytes();
-  return peer_barrier(ctx);
-}
-
-extern "C" int iqsb_swap2x2_global(iqsb_state *st, unsigned M, unsigned pos1, unsigned pos2, const double m[8]) {
-  IQSB_REQUIRE(st && m, "iqsb_swap2x2_global: null argument");
-  iqsb_ctx *ctx = st->ctx;
-  IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_swap2x2_global: register is not shared across ranks");
-  IQSB_REQUIRE(M == st->log2_local && pos1 < pos2 && pos2 >= M && (1u << (pos2 - M)) < (unsigned)ctx->nranks,
-               "iqsb_swap2x2_global: need pos1 < pos2, pos2 global");
-  IQSB_TRY(peer_barrier(ctx));
-  int rc = IQSB_OK;
-  if (pos1 < M) {
-    // i0 = base + 2^pos1 lives on the rank whose pos2 bit is 0 (A); i1 = base + 2^pos2 on its
-    // partner (B) at local index base.  (reference qureg_applyswap.cpp:170-206, 292-400)
-    unsigned rb = pos2 - M;
-    int partner = ctx->rank ^ (1 << rb);
-    unsigned mybit = (ctx->rank >> rb) & 1;
-    void *s0 = mybit ? st->peer_ptr[partner] : st->d;
-    void *s1 = mybit ? st->d : st->peer_ptr[partner];
-    int sb = pick_split_bit(M, (int)pos1, -1);
-    if (sb < 0) {
-      unsigned p[1] = {pos1}, v[1] = {0};
-      rc = mybit ? IQSB_OK : launch_split(st, s0, s1, 1, p, v, 1ull << pos1, 0, m);
-    } else {
-      unsigned p[2] = {pos1, (unsigned)sb}, v[2] = {0, mybit ? 0u : 1u};
-      rc = launch_split(st, s0, s1, 2, p, v, 1ull << pos1, 0, m);
-    }
-    ctx->nvlink_bytes += st->local_amps / 2 * st->amp_bytes();
-  } else {
-    unsigned r1 = pos1 - M, r2 = pos2 - M;
-    unsigned b1 = (ctx->rank >> r1) & 1, b2 = (ctx->rank >> r2) & 1;
-    if (b1 != b2) {
-      int partner = ctx->rank ^ (1 << r1) ^ (1 << r2);
-      bool iamA = (b1 == 1);  // A holds i0 (pos1 bit 1, pos2 bit 0)
-      void *s0 = iamA ? st->d : st->peer_ptr[partner];
-      void *s1 = iamA ? st->peer_ptr[partner] : st->d;
-      int sb = pick_split_bit(M, -1, -1);
-      if (sb < 0) {
-        rc = iamA ? launch_split(st, s0, s1, 0, nullptr, nullptr, 0, 0, m) : IQSB_OK;
-      } else {
-        unsigned p[1] = {(unsigned)sb}, v[1] = {iamA ? 1u : 0u};
-        rc = launch_split(st, s0, s1, 1, p, v, 0, 0, m);
-      }
-      ctx->nvlink_bytes += st->local_amps * st->amp_bytes();
-    }
-  }
-  IQSB_TRY(rc);
   return peer_barrier(ctx);
 }
 

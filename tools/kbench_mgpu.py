@@ -1,6 +1,6 @@
 """NVLink-side kernel timing: gates on global qubits through the C ABI, one process per GPU.
 
-launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/kbench_mgpu.py [--m 30]
+launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/kbench_mgpu.py [--local-qubits 30]
 Reports, per op, ms (max over ranks), algorithmic NVLink GB/s per GPU per direction and
 the fraction of the measured 770 GB/s peer-copy reference / 900 GB/s nominal.
 """
@@ -24,7 +24,7 @@ capi, C = pkg.capi, pkg.circuits
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--m", type=int, default=30, help="local qubits per GPU")
+    ap.add_argument("--local-qubits", dest="m", type=int, default=30, help="local qubits per GPU")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default=None)
     a = ap.parse_args()

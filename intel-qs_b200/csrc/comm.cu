@@ -68,6 +68,26 @@ __global__ void __launch_bounds__(256) k_copy_chunks(const Chunk<T> *__restrict_
   for (uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += stride) st_chunk(dst + t, ld_chunk(src + t));
 }
 
+// exchange two equally sized chunk ranges (one may be remote): pure data movement
+template <typename T>
+__global__ void __launch_bounds__(256) k_xchg_chunks(Chunk<T> *a, Chunk<T> *b, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * 256;
+  uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  for (; t + stride < n; t += 2 * stride) {
+    Chunk<T> x0 = ld_chunk(a + t), y0 = ld_chunk(b + t);
+    Chunk<T> x1 = ld_chunk(a + t + stride), y1 = ld_chunk(b + t + stride);
+    st_chunk(a + t, y0);
+    st_chunk(b + t, x0);
+    st_chunk(a + t + stride, y1);
+    st_chunk(b + t + stride, x1);
+  }
+  for (; t < n; t += stride) {
+    Chunk<T> x = ld_chunk(a + t), y = ld_chunk(b + t);
+    st_chunk(a + t, y);
+    st_chunk(b + t, x);
+  }
+}
+
 }  // namespace
 
 static int allgather_bytes64(iqsb_ctx *ctx, const void *mine64, void *all_host) {
@@ -358,6 +378,30 @@ extern "C" int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank) {
   iqsb_ctx *ctx = st->ctx;
   IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_permute_global: register is not shared across ranks");
   IQSB_REQUIRE(src_rank >= 0 && src_rank < ctx->nranks && dst_rank >= 0 && dst_rank < ctx->nranks, "iqsb_permute_global: bad ranks");
+  uint64_t Lall = st->local_amps;
+  // Fast path: when every rank is a fixed point or half of a 2-cycle (e.g. reversing the order of the
+  // global qubits), partners exchange their shards in place with one kernel each -- the lower rank
+  // swaps the upper half, the higher rank the lower half -- without staging.  All ranks must take the
+  // same path (the rendezvous counts differ), so they agree through a 1-double all-reduce.
+  {
+    double not_simple = (src_rank == dst_rank) ? 0.0 : 1.0;
+    IQSB_TRY(iqsb_allreduce_f64(ctx, &not_simple, 1, IQSB_MAX));
+    if (not_simple == 0.0 && Lall >= 4) {
+      IQSB_TRY(peer_barrier(ctx));
+      if (src_rank != ctx->rank) {
+        uint64_t half_chunks = Lall / 4;  // chunks in half a shard
+        uint64_t first = ctx->rank < src_rank ? half_chunks : 0;
+        char *mine = (char *)st->d + first * 2 * st->amp_bytes();
+        char *theirs = (char *)st->peer_ptr[src_rank] + first * 2 * st->amp_bytes();
+        int grid = ctx->num_sms * 8;
+        if (st->dtype == IQSB_F64) k_xchg_chunks<double><<<grid, 256, 0, ctx->stream>>>((Chunk<double> *)mine, (Chunk<double> *)theirs, half_chunks);
+        else k_xchg_chunks<float><<<grid, 256, 0, ctx->stream>>>((Chunk<float> *)mine, (Chunk<float> *)theirs, half_chunks);
+        IQSB_TRY(iqsb_check_launch(ctx, "k_xchg_chunks"));
+        ctx->nvlink_bytes += Lall * st->amp_bytes();
+      }
+      return peer_barrier(ctx);
+    }
+  }
   // Every shard is both a source and a destination, so the move is staged through the tmp area
   // in chunks (as the reference does, qureg_permute.cpp:174-185), pulling with peer loads.
   uint64_t L = st->local_amps, chunk = st->tmp_amps;

@@ -156,7 +156,15 @@ Environment::Environment() : inited_(true) {
   shared_instance = this;
 }
 Environment::~Environment() {
-  if (shared_instance == this) shared_instance = nullptr;
+  // like the reference's destructor (MPI_Finalize): the last act of a program.  Tearing the NCCL
+  // communicator and the IPC mappings down here keeps process exit fast and orderly.
+  if (shared_instance == this) {
+    shared_instance = nullptr;
+    if (g_ctx) {
+      iqsb_finalize(g_ctx);
+      g_ctx = nullptr;
+    }
+  }
 }
 
 void Environment::Init() {

@@ -436,3 +436,42 @@ def test_large_state_properties(gpu_ctx):
     assert a.equal(b)
     a.free()
     b.free()
+
+
+def test_full_size_32_qubits_properties(gpu_ctx):
+    """BASELINE configs[1] size (2^32 amplitudes, 64 GiB per register): size-independent properties.
+    Skipped when the device cannot hold two registers."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    n = 32
+    if free < 2 * 16 * (1 << n) + (4 << 30):
+        pytest.skip("needs ~132 GiB of free HBM")
+    a, b = gpu_ctx.alloc(1 << n), gpu_ctx.alloc(1 << n)
+    a.fill_random(99)
+    a.scale(1.0 / math.sqrt(a.norm2()))
+    b.copy_from(a)
+    g = C.G_FIXED.view(np.complex128).reshape(2, 2)
+    gd = np.ascontiguousarray(g.conj().T)
+    for pos in (0, 1, 16, 30, 31):
+        a.gate1(pos, g)
+    a.cgate1(31, 0, X)
+    a.cgate1(0, 31, X)
+    assert abs(a.norm2() - 1.0) < 1e-12  # unitarity at full size
+    a.cgate1(0, 31, X)
+    a.cgate1(31, 0, X)
+    for pos in (31, 30, 16, 1, 0):
+        a.gate1(pos, gd)
+    assert a.maxabsdiff(b) < 1e-12  # G then G^dagger restores every amplitude
+    a.copy_from(b)
+    a.swap2x2(0, 31, X)
+    a.swap2x2(7, 30, X)
+    a.swap2x2(7, 30, X)
+    a.swap2x2(0, 31, X)
+    assert a.equal(b)  # data movement round trip is bit exact
+    # linearity: P(bit 31 = 1) after H on 31 of the uniform state is 0
+    a.fill_const(1.0 / math.sqrt(float(1 << n)))
+    a.gate1(31, HM)
+    assert abs(a.prob1(31)) < 1e-12 and abs(a.norm2() - 1.0) < 1e-12
+    a.free()
+    b.free()

@@ -69,6 +69,7 @@ def main():
     timeit("swap_global(local M-1, glob)", lambda: st.swap2x2_global(M, M - 1, M + k - 1, X), 8.0 * L)
     if k >= 2:
         timeit("swap_global(glob, glob)", lambda: st.swap2x2_global(M, M, M + 1, X), 16.0 * L)
+    timeit("permute_global(pair swap)", lambda: st.permute_global(rank ^ 1, rank ^ 1), 16.0 * L)
     timeit("permute_global(shift 1)", lambda: st.permute_global((rank + 1) % world, (rank - 1) % world), 16.0 * L)
     timeit("local gate1(pos 10) [ref]", lambda: st.gate1(10, C.G_FIXED), 32.0 * L)
     if rank == 0 and a.out:

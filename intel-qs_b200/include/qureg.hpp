@@ -302,3 +302,7 @@ template <typename Type>
 using BaseType = typename QubitRegister<Type>::BaseType;
 
 }  // namespace iqs
+
+// Derived class that counts gates and depth (as the reference does at the end of qureg.hpp).
+// NoisyQureg (automatic noise insertion) is outside the B200 scope and is not provided.
+#include "QubitRegisterMetric.hpp"

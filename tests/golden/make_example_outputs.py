@@ -1,0 +1,29 @@
+"""Capture the stdout of the reference's own programs built against the UNMODIFIED reference library
+(oracle/_ref/refbin/*, see oracle/Makefile) as fixtures for tests/test_examples_dropin_gpu.py.
+Run in the build container: python tests/golden/make_example_outputs.py"""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+BIN = os.path.join(ROOT, "oracle", "_ref", "refbin")
+
+COMMANDS = {
+    "grover_4qubit": [],
+    "expect_value_test": [],
+    "heisenberg_dynamics": ["8"],
+    "quantum_fourier_transform": ["8"],
+    "test_of_custom_gates": ["10"],
+    "benchgates": ["10"],
+    "specv2_bench": ["10", "1"],
+    "get_started_with_IQS": [],
+    "communication_reduction_via_qubit_reordering": ["22"],
+}
+
+if __name__ == "__main__":
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    for name, args in COMMANDS.items():
+        r = subprocess.run([os.path.join(BIN, name)] + args, capture_output=True, text=True, env=env, timeout=600)
+        # (benchgates ends with `return 1` also on success; the exit code is part of the fixture)
+        open(os.path.join(HERE, "examples", name + ".txt"), "w").write(f"EXIT {r.returncode}\n" + r.stdout)
+        print(name, "exit", r.returncode, len(r.stdout.splitlines()), "lines")

@@ -247,3 +247,9 @@ void BcastDouble(double *inout, int n, int root) {
 
 }  // namespace mpi
 }  // namespace iqs
+
+#include "../include/qureg_version.hpp"
+namespace iqs {
+// the QASM interface prints this string (interface/src/interface_api_version.cpp:16-21); it names the API level
+std::string GetQhipsterVersion() { return QHIPSTER_VERSION_STRING; }
+}  // namespace iqs

@@ -20,8 +20,14 @@ COMMANDS = {
     "communication_reduction_via_qubit_reordering": ["22"],
 }
 
+# the QASM interpreter reads its program from stdin (interface/src/interface_api_qasm.cpp:109-125)
+QASM = ".malloc 3\nH q0\nCNOT q0,q1\nT q1\nS q2\nX q2\nTdag q0\nMeasZ q0\nMeasZ q1\nMeasZ q2\n.version\n.free\n\n"
+
 if __name__ == "__main__":
     env = dict(os.environ, OMP_NUM_THREADS="4")
+    r = subprocess.run([os.path.join(BIN, "iqs_interface")], input=QASM, capture_output=True, text=True, env=env, timeout=600)
+    open(os.path.join(HERE, "examples", "iqs_interface.txt"), "w").write(f"EXIT {r.returncode}\n" + r.stdout)
+    print("iqs_interface exit", r.returncode)
     for name, args in COMMANDS.items():
         r = subprocess.run([os.path.join(BIN, name)] + args, capture_output=True, text=True, env=env, timeout=600)
         # (benchgates ends with `return 1` also on success; the exit code is part of the fixture)

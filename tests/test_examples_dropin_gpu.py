@@ -22,11 +22,11 @@ NUM = re.compile(r"[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eE][-+]?\d+)?")
 SKIP = re.compile(r"seconds|Simulation time|OMP number of threads|statistics|IqsMPI|INTELQS_HAS_MPI|Fusion is|Compiler flags|-->|Time |time ", re.I)
 
 
-def run(name, args):
+def run(name, args, stdin=None):
     exe = os.path.join(BIN, name)
     if not os.path.exists(exe):
         pytest.skip(f"{exe} not built (needs /root/reference at build time)")
-    r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe] + args, input=stdin, capture_output=True, text=True, timeout=600)
     return r.returncode, r.stdout, r.stderr
 
 
@@ -48,9 +48,9 @@ def same(a, b, tol):
     return len(xa) == len(xb) and all(abs(p - q) <= tol for p, q in zip(xa, xb))
 
 
-def compare(name, args, tol=1e-7, rc_must_match=True):
+def compare(name, args, tol=1e-7, rc_must_match=True, stdin=None):
     want_rc, want = golden(name)
-    rc, out, err = run(name, args)
+    rc, out, err = run(name, args, stdin)
     if rc_must_match:
         assert rc == want_rc, f"{name}: exit {rc}, reference exits {want_rc}\n{err[-1500:]}"
     got, want = keep(out.splitlines()), keep(want)
@@ -110,3 +110,9 @@ def test_quantum_fourier_transform_example():
     _, want = golden("quantum_fourier_transform")
     wdp = [l for l in want if l.startswith("DP::qufft")][0]
     assert abs(float(dp.group(1)) - float(re.search(r"absdiff: ([0-9.eE+-]+)", wdp).group(1))) < 1e-15
+
+
+def test_qasm_interface():
+    """interface/src/*.cpp, the stdin QASM interpreter, relinked unchanged."""
+    qasm = ".malloc 3\nH q0\nCNOT q0,q1\nT q1\nS q2\nX q2\nTdag q0\nMeasZ q0\nMeasZ q1\nMeasZ q2\n.version\n.free\n\n"
+    compare("iqs_interface", [], stdin=qasm)

@@ -16,9 +16,9 @@ import math
 import numpy as np
 
 OP_DTYPE = np.dtype(
-    [("kind", "<i4"), ("q0", "<i4"), ("q1", "<i4"), ("q2", "<i4"), ("p", "<f8", (32,))], align=False
+    [("kind", "<i4"), ("q0", "<i4"), ("q1", "<i4"), ("q2", "<i4"), ("p", "<f8", (40,))], align=False
 )
-assert OP_DTYPE.itemsize == 272
+assert OP_DTYPE.itemsize == 336
 
 HEADER_DTYPE = np.dtype(
     [("magic", "<u4"), ("num_qubits", "<u4"), ("nops", "<u4"), ("init", "<u4"), ("base_index", "<u8"), ("reserved", "<u8")]
@@ -89,7 +89,7 @@ class Program:
         return self._add(PROB, q)
 
     def expect(self, qubits, observables):
-        p = np.zeros(32)
+        p = np.zeros(40)
         p[: len(qubits)] = qubits
         p[16 : 16 + len(observables)] = observables
         return self._add(EXPECT, len(qubits), p=p)

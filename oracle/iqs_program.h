@@ -17,7 +17,7 @@
 typedef struct iqs_op {
   int32_t kind;
   int32_t q0, q1, q2;
-  double p[32]; /* matrix (row-major, re/im interleaved), angles, or a qubit map */
+  double p[40]; /* matrix (row-major, re/im interleaved), angles, or a qubit map (<= 40 qubits) */
 } iqs_op;
 
 enum {

@@ -19,7 +19,9 @@
 //
 // NCCL is used for the bootstrap (all-gather of IPC handles) and the scalar collectives.
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
+#include <sys/time.h>
 
 #include "iqsb_internal.cuh"
 
@@ -119,8 +121,31 @@ static int open_peers(iqsb_ctx *ctx, void *mine, void **out_ptrs) {
   return IQSB_OK;
 }
 
+static void trace_init(const char *what) {  // IQS_B200_TRACE=1: bootstrap phase timestamps on stderr
+  static const bool on = getenv("IQS_B200_TRACE") != nullptr;
+  if (!on) return;
+  struct timeval tv;
+  gettimeofday(&tv, nullptr);
+  fprintf(stderr, "[iqsb %ld.%03ld] %s\n", (long)tv.tv_sec % 1000, (long)tv.tv_usec / 1000, what);
+}
+
+// The ranks of one job live on one NVSwitch box and NCCL only carries the bootstrap and a few
+// scalars, so unless the user says otherwise it is told to rendezvous over loopback and not to
+// probe InfiniBand / network plugins (measured: the probing made ncclCommInitRank take 25-185 s on
+// the pool's boxes; with these defaults it takes about a second).
+static void nccl_single_node_defaults() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  setenv("NCCL_SOCKET_IFNAME", "lo", 0);
+  setenv("NCCL_IB_DISABLE", "1", 0);
+  setenv("NCCL_NET_PLUGIN", "none", 0);
+  setenv("NCCL_TUNER_PLUGIN", "none", 0);
+}
+
 extern "C" int iqsb_unique_id(void *out_128_bytes) {
   IQSB_REQUIRE(out_128_bytes, "iqsb_unique_id: null argument");
+  nccl_single_node_defaults();
   static_assert(sizeof(ncclUniqueId) == IQSB_UNIQUE_ID_BYTES, "ncclUniqueId size");
   ncclUniqueId id;
   IQSB_NCCL(ncclGetUniqueId(&id));
@@ -133,7 +158,10 @@ int iqsb_comm_init(iqsb_ctx *ctx, const void *uid) {
   ctx->peers = pt;
   ncclUniqueId id;
   memcpy(&id, uid, sizeof(id));
+  nccl_single_node_defaults();
+  trace_init("ncclCommInitRank ...");
   IQSB_NCCL(ncclCommInitRank(&pt->comm, ctx->nranks, id, ctx->rank));
+  trace_init("ncclCommInitRank done");
   ctx->comm = pt->comm;
   IQSB_CUDA(cudaMalloc(&pt->d_coll, sizeof(double) * kMaxCollDoubles));
   IQSB_CUDA(cudaMalloc(&pt->d_handles, 64 * ctx->nranks));
@@ -143,9 +171,11 @@ int iqsb_comm_init(iqsb_ctx *ctx, const void *uid) {
   IQSB_TRY(open_peers(ctx, pt->flags_local, (void **)pt->flags_peer));
   IQSB_CUDA(cudaMalloc(&pt->d_flags_peer, sizeof(uint32_t *) * ctx->nranks));
   IQSB_CUDA(cudaMemcpy(pt->d_flags_peer, pt->flags_peer, sizeof(uint32_t *) * ctx->nranks, cudaMemcpyHostToDevice));
+  trace_init("peer flags mapped");
   // nobody may signal before everyone has zeroed and mapped the flags
   IQSB_NCCL(ncclAllReduce(pt->d_coll, pt->d_coll, 1, ncclDouble, ncclSum, pt->comm, ctx->stream));
   IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
+  trace_init("first all-reduce done");
   return IQSB_OK;
 }
 

@@ -125,8 +125,17 @@ static bool write_file(const char *fn, const void *p, size_t bytes) {
   return w == bytes;
 }
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static void trace(const char *what) {  // IQS_DRIVER_TRACE=1: phase timestamps on stderr
+  static const bool on = getenv("IQS_DRIVER_TRACE") != nullptr;
+  static double t0 = now_s();
+  if (on) fprintf(stderr, "[driver %6.3f s] %s\n", now_s() - t0, what);
+}
+
 int main(int argc, char **argv) {
+  trace("start");
   iqs::mpi::Environment env(argc, argv, false);
+  trace("environment ready");
   if (env.IsUsefulRank() == false) return 0;
   if (argc < 2) {
     fprintf(stderr, "usage: %s program.bin [--state-in f] [--state-out f] [--scalars-out f] [--map-out f] [--repeat R]\n", argv[0]);
@@ -180,8 +189,10 @@ int main(int argc, char **argv) {
     fclose(s);
   }
 
+  trace("register initialised");
   std::vector<double> scalars;
   psi.ComputeNorm();  // settle the state in its home memory before the clock starts
+  trace("first reduction done");
   auto t0 = std::chrono::steady_clock::now();
   if (!step_sizes.empty()) {
     // timed step by step: one "STEP i seconds" line each (ComputeNorm closes a step so that
@@ -208,6 +219,7 @@ int main(int argc, char **argv) {
   if (iqs::mpi::Environment::GetStateRank() == 0)
     printf("TIME %.6f OPS %zu NORM %.15f\n", secs, ops.size() * (size_t)repeat, nrm);
 
+  trace("program done");
   int rank = iqs::mpi::Environment::GetStateRank(), nranks = iqs::mpi::Environment::GetStateSize();
   if (state_out) {
     // every rank writes its shard at its offset (rank 0 first creates the file)
@@ -229,6 +241,7 @@ int main(int argc, char **argv) {
       iqs::mpi::StateBarrier();
     }
   }
+  trace("state written");
   if (rank == 0 && scalars_out) write_file(scalars_out, scalars.data(), scalars.size() * sizeof(double));
   if (rank == 0 && map_out) {
     std::vector<uint64_t> map(n);

@@ -203,6 +203,8 @@ def run_driver(driver, program, state=None, init=1, base_index=0, threads=None, 
         for line in r.stdout.splitlines():
             if line.startswith("TIME "):
                 secs = float(line.split()[1])
+        if env.get("IQS_DRIVER_TRACE"):
+            print(r.stderr)
         out = {"seconds": secs, "stdout": r.stdout}
         out["scalars"] = np.fromfile(os.path.join(td, "scal.bin"), dtype=np.float64) if os.path.exists(os.path.join(td, "scal.bin")) else np.zeros(0)
         out["map"] = np.fromfile(os.path.join(td, "map.bin"), dtype=np.uint64).astype(np.int64)

@@ -58,6 +58,8 @@ int iqsb_rank(const iqsb_ctx *ctx);
 int iqsb_nranks(const iqsb_ctx *ctx);
 int iqsb_device(const iqsb_ctx *ctx);
 int iqsb_sync(iqsb_ctx *ctx);
+/* free and total HBM of the context's device, in bytes */
+int iqsb_mem_info(iqsb_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
 /* adopt an external cudaStream_t (e.g. torch's current stream) so that the caller's
  * CUDA events bracket our launches; NULL restores the context's own stream. */
 int iqsb_set_stream(iqsb_ctx *ctx, void *cuda_stream);

@@ -59,7 +59,7 @@ def build_cuda(verbose=False):
         list(ex.map(_run, jobs))
     so = os.path.join(LIB, "libiqs_b200.so")
     if jobs or _newer(so, objs):
-        _run([NVCC, "-shared", "-ccbin", CXX, "-Wno-deprecated-gpu-targets", "-o", so] + objs + ["-lnccl"])
+        _run([NVCC, "-shared", "-ccbin", CXX, "-Wno-deprecated-gpu-targets", "-o", so] + objs + ["-ldl"])
     if verbose:
         print(f"[build] {so} ({len(jobs)} objects recompiled)")
     return so

@@ -61,6 +61,7 @@ def load():
         "iqsb_finalize": [c_vp],
         "iqsb_rank": [c_vp], "iqsb_nranks": [c_vp], "iqsb_device": [c_vp],
         "iqsb_sync": [c_vp],
+        "iqsb_mem_info": [c_vp, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)],
         "iqsb_set_stream": [c_vp, c_vp], "iqsb_get_stream": [c_vp],
         "iqsb_launch_count": [c_vp], "iqsb_nvlink_bytes": [c_vp],
         "iqsb_timer_start": [c_vp], "iqsb_timer_stop": [c_vp, ctypes.POINTER(c_dbl)],
@@ -162,6 +163,11 @@ class Context:
 
     def sync(self):
         _chk(self.L.iqsb_sync(self.h))
+
+    def mem_info(self):
+        f, t = c_u64(), c_u64()
+        _chk(self.L.iqsb_mem_info(self.h, ctypes.byref(f), ctypes.byref(t)))
+        return int(f.value), int(t.value)
 
     def set_stream(self, cuda_stream_ptr):
         _chk(self.L.iqsb_set_stream(self.h, c_vp(cuda_stream_ptr)))

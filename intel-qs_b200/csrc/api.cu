@@ -108,6 +108,16 @@ extern "C" int iqsb_sync(iqsb_ctx *ctx) {
   return IQSB_OK;
 }
 
+extern "C" int iqsb_mem_info(iqsb_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes) {
+  IQSB_REQUIRE(ctx && free_bytes && total_bytes, "iqsb_mem_info: null argument");
+  size_t f = 0, t = 0;
+  IQSB_CUDA(cudaSetDevice(ctx->device));
+  IQSB_CUDA(cudaMemGetInfo(&f, &t));
+  *free_bytes = f;
+  *total_bytes = t;
+  return IQSB_OK;
+}
+
 extern "C" int iqsb_set_stream(iqsb_ctx *ctx, void *cuda_stream) {
   IQSB_REQUIRE(ctx, "iqsb_set_stream: null context");
   IQSB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -18,12 +18,58 @@
 // 1-qubit gate on a global qubit.
 //
 // NCCL is used for the bootstrap (all-gather of IPC handles) and the scalar collectives.
+#include <dlfcn.h>
 #include <nccl.h>
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
 
 #include "iqsb_internal.cuh"
+
+// NCCL is resolved at run time, and only when a job has more than one rank: a single-rank process
+// never loads it, and a process that already holds an NCCL (e.g. the one bundled with PyTorch) keeps
+// using that copy instead of pulling a second libnccl.so.2 into the address space.
+namespace nccl_dyn {
+ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+const char *(*GetErrorString)(ncclResult_t) = nullptr;
+static bool load() {
+  if (GetUniqueId) return true;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    iqsb_set_error("cannot load libnccl.so.2: %s", dlerror());
+    return false;
+  }
+#define IQSB_SYM(field, name)                                  \
+  *(void **)(&field) = dlsym(h, name);                         \
+  if (!field) {                                                \
+    iqsb_set_error("libnccl.so.2 has no symbol %s", name);     \
+    GetUniqueId = nullptr;                                     \
+    return false;                                              \
+  }
+  IQSB_SYM(CommInitRank, "ncclCommInitRank")
+  IQSB_SYM(CommDestroy, "ncclCommDestroy")
+  IQSB_SYM(AllGather, "ncclAllGather")
+  IQSB_SYM(AllReduce, "ncclAllReduce")
+  IQSB_SYM(Broadcast, "ncclBroadcast")
+  IQSB_SYM(GetErrorString, "ncclGetErrorString")
+  IQSB_SYM(GetUniqueId, "ncclGetUniqueId")
+#undef IQSB_SYM
+  return true;
+}
+}  // namespace nccl_dyn
+#define ncclGetUniqueId nccl_dyn::GetUniqueId
+#define ncclCommInitRank nccl_dyn::CommInitRank
+#define ncclCommDestroy nccl_dyn::CommDestroy
+#define ncclAllGather nccl_dyn::AllGather
+#define ncclAllReduce nccl_dyn::AllReduce
+#define ncclBroadcast nccl_dyn::Broadcast
+#define ncclGetErrorString nccl_dyn::GetErrorString
 
 #define IQSB_NCCL(call)                                                                      \
   do {                                                                                       \
@@ -146,6 +192,7 @@ static void nccl_single_node_defaults() {
 extern "C" int iqsb_unique_id(void *out_128_bytes) {
   IQSB_REQUIRE(out_128_bytes, "iqsb_unique_id: null argument");
   nccl_single_node_defaults();
+  if (!nccl_dyn::load()) return IQSB_ERR_NCCL;
   static_assert(sizeof(ncclUniqueId) == IQSB_UNIQUE_ID_BYTES, "ncclUniqueId size");
   ncclUniqueId id;
   IQSB_NCCL(ncclGetUniqueId(&id));
@@ -159,6 +206,7 @@ int iqsb_comm_init(iqsb_ctx *ctx, const void *uid) {
   ncclUniqueId id;
   memcpy(&id, uid, sizeof(id));
   nccl_single_node_defaults();
+  if (!nccl_dyn::load()) return IQSB_ERR_NCCL;
   trace_init("ncclCommInitRank ...");
   IQSB_NCCL(ncclCommInitRank(&pt->comm, ctx->nranks, id, ctx->rank));
   trace_init("ncclCommInitRank done");

@@ -80,6 +80,59 @@ __global__ void __launch_bounds__(kBlock)
   }
 }
 
+// ---- exchange the two partners without arithmetic (exact Pauli X on the pair: SWAP, CNOT data
+// movement, the transpositions of a qubit permutation): bit-for-bit moves ------------------------
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_move_w2(Chunk<T> *s0, Chunk<T> *s1, Geom g) {
+  uint64_t t0 = ((uint64_t)blockIdx.x * kUnroll) * kBlock + threadIdx.x;
+  Chunk<T> v0[kUnroll], v1[kUnroll];
+  uint64_t i0[kUnroll], i1[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      uint64_t x = expand(t, g);
+      i0[u] = x + g.off0;
+      i1[u] = x + g.off1;
+      v0[u] = ld_chunk(s0 + i0[u]);
+      v1[u] = ld_chunk(s1 + i1[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      st_chunk(s0 + i0[u], v1[u]);
+      st_chunk(s1 + i1[u], v0[u]);
+    }
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_move_w1(Cx<T> *s0, Cx<T> *s1, Geom g) {
+  uint64_t t0 = ((uint64_t)blockIdx.x * kUnroll) * kBlock + threadIdx.x;
+  Cx<T> v0[kUnroll], v1[kUnroll];
+  uint64_t i0[kUnroll], i1[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      uint64_t x = expand(t, g);
+      i0[u] = x + g.off0;
+      i1[u] = x + g.off1;
+      v0[u] = ld_amp(s0 + i0[u]);
+      v1[u] = ld_amp(s1 + i1[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t t = t0 + (uint64_t)u * kBlock;
+    if (t < g.nwork) {
+      st_amp(s0 + i0[u], v1[u]);
+      st_amp(s1 + i1[u], v0[u]);
+    }
+  }
+}
+
 // ---- target position 0: both partners live in one chunk -------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_inchunk(Chunk<T> *__restrict__ s, Geom g, Mat2<T> m) {
@@ -289,6 +342,19 @@ int iqsb_launch_pairs(iqsb_state *st, void *s0, void *s1, int width, const Geom 
   if (g.nwork == 0) return IQSB_OK;
   iqsb_ctx *ctx = st->ctx;
   unsigned grid = (unsigned)div_up(g.nwork, (uint64_t)kBlock * kUnroll);
+  // exact Pauli X on the pair = exchange of the two partners: no arithmetic (the reference's
+  // 0*a + 1*b gives the same values; only the sign of a zero could differ)
+  const bool is_x = m[0] == 0. && m[1] == 0. && m[2] == 1. && m[3] == 0. && m[4] == 1. && m[5] == 0. && m[6] == 0. && m[7] == 0.;
+  if (is_x) {
+    if (st->dtype == IQSB_F64) {
+      if (width == 2) k_move_w2<double><<<grid, kBlock, 0, ctx->stream>>>((Chunk<double> *)s0, (Chunk<double> *)s1, g);
+      else k_move_w1<double><<<grid, kBlock, 0, ctx->stream>>>((Cx<double> *)s0, (Cx<double> *)s1, g);
+    } else {
+      if (width == 2) k_move_w2<float><<<grid, kBlock, 0, ctx->stream>>>((Chunk<float> *)s0, (Chunk<float> *)s1, g);
+      else k_move_w1<float><<<grid, kBlock, 0, ctx->stream>>>((Cx<float> *)s0, (Cx<float> *)s1, g);
+    }
+    return iqsb_check_launch(ctx, "k_move");
+  }
   if (st->dtype == IQSB_F64) {
     if (width == 2)
       k_pairs_w2<double><<<grid, kBlock, 0, ctx->stream>>>((Chunk<double> *)s0, (Chunk<double> *)s1, g,

@@ -161,12 +161,25 @@ extern "C" int iqsb_permute_local(iqsb_state *st, const uint8_t *dst_bit, unsign
   if (identity) return IQSB_OK;
   iqsb_ctx *ctx = st->ctx;
   size_t bytes = st->local_amps * st->amp_bytes();
+  // A bit permutation is a product of (nbits - #cycles) transpositions, and a transposition is a
+  // SWAP sweep that moves half of the shard in place (16*L bytes, no scratch).  The out-of-place
+  // gather below costs a read of scattered 16/32-byte pieces plus two more passes for the copy back
+  // and needs a second shard of HBM; measured at 2^32 amplitudes a full bit reversal takes 250 ms that
+  // way against ~10 ms per transposition.  So: transpositions unless there are very many of them.
+  unsigned transpositions = 0;
+  {
+    uint64_t visited = 0;
+    for (unsigned b = 0; b < nbits; ++b) {
+      if ((visited >> b) & 1) continue;
+      unsigned len = 0;
+      for (unsigned c = b; !((visited >> c) & 1); c = dst_bit[c]) { visited |= 1ull << c; ++len; }
+      transpositions += len - 1;
+    }
+  }
   void *scratch = nullptr;
-  cudaError_t e = cudaMalloc(&scratch, bytes);
+  cudaError_t e = transpositions <= 24 ? cudaErrorMemoryAllocation : cudaMalloc(&scratch, bytes);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
-    // Not enough HBM for an out-of-place pass (shards above ~85 GiB): decompose into
-    // transpositions and run each as a bit-exact SWAP sweep (16*L bytes each).
     uint8_t cur[64];  // cur[b] = destination still owed by the data sitting at source bit b
     for (unsigned b = 0; b < nbits; ++b) cur[b] = dst_bit[b];
     const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};

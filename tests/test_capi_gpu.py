@@ -441,9 +441,7 @@ def test_large_state_properties(gpu_ctx):
 def test_full_size_32_qubits_properties(gpu_ctx):
     """BASELINE configs[1] size (2^32 amplitudes, 64 GiB per register): size-independent properties.
     Skipped when the device cannot hold two registers."""
-    import torch
-
-    free, _ = torch.cuda.mem_get_info()
+    free, _ = gpu_ctx.mem_info()
     n = 32
     if free < 2 * 16 * (1 << n) + (4 << 30):
         pytest.skip("needs ~132 GiB of free HBM")

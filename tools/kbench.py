@@ -33,7 +33,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--mem", default="device")
     ap.add_argument("--out", default=None)
-    ap.add_argument("--ops", default="gate1,cgate1,swap,diag,phase,prob,norm,parity,fused,gate2,collapse")
+    ap.add_argument("--ops", default="gate1,cgate1,swap,diag,phase,prob,norm,parity,fused,gate2,collapse,permute")
     a = ap.parse_args()
     n = a.n
     L = 1 << n
@@ -96,6 +96,12 @@ def main():
         q, _ = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))
         for ph, pl in [(1, 0), (0, 1), (5, 3), (n - 1, 2)]:
             timeit("gate2", (ph, pl), lambda ph=ph, pl=pl: st.gate2(ph, pl, q), 32.0 * L)
+    if "permute" in ops:
+        rev = list(range(n))[::-1]
+        rot = [(b + 1) % n for b in range(n)]
+        low = list(range(n)); low[1], low[n - 2] = low[n - 2], low[1]
+        for name, perm in (("reverse", rev), ("rotate1", rot), ("swap(1,n-2)", low)):
+            timeit("permute", name, lambda perm=perm: st.permute_local(perm), 32.0 * L)
     if "collapse" in ops:
         for pos in (0, 5, n - 1):
             timeit("collapse", pos, lambda pos=pos: st.collapse(pos, 1), 8.0 * L)

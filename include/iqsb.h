@@ -176,6 +176,10 @@ int iqsb_axpy(iqsb_state *a, const iqsb_state *b, const double f[2]);
 /* ---- qubit reordering: PermuteLocalQubits (src/qureg_permute.cpp:55-104) ------------- */
 /* new[j] = old[i] where bit b of i becomes bit dst_bit[b] of j, b < log2(local_amps). */
 int iqsb_permute_local(iqsb_state *st, const uint8_t *dst_bit, unsigned nbits);
+/* Pure host function: the in-place tile phases iqsb_permute_local runs for this permutation.  Phase p:
+ * out[25p] = number of tile positions nS, out[25p+1..] = the positions (ascending), out[25p+13..] = for
+ * tile-local bit k the tile-local bit it moves to.  Used by the CPU tests of the planner. */
+int iqsb_plan_permute(const uint8_t *dst_bit, unsigned nbits, uint8_t *out, int max_phases, int *nphases);
 
 /* ---- distributed (nranks > 1): fused compute + NVLink peer access -------------------- */
 /* Pure host function (no GPU needed): which pairs of a gate on a global qubit THIS rank updates.

@@ -37,6 +37,19 @@ def plan_global(kind, rank, nranks, M, pos1, pos2):
     return pl
 
 
+def plan_permute(dst_bit):
+    """Host-only: list of (positions, dstslot) tile phases for a local qubit permutation."""
+    a = np.ascontiguousarray(dst_bit, dtype=np.uint8)
+    out = np.zeros(64 * 25, dtype=np.uint8)
+    n = c_int()
+    _chk(load().iqsb_plan_permute(a.ctypes.data_as(c_vp), a.size, out.ctypes.data_as(c_vp), 64, ctypes.byref(n)))
+    phases = []
+    for p in range(n.value):
+        ns = int(out[25 * p])
+        phases.append((out[25 * p + 1 : 25 * p + 1 + ns].astype(int).tolist(), out[25 * p + 13 : 25 * p + 13 + ns].astype(int).tolist()))
+    return phases
+
+
 class FGate(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int32), ("control", ctypes.c_int32), ("target", ctypes.c_int32), ("pad", ctypes.c_int32), ("m", c_dbl * 8)]
 
@@ -101,6 +114,7 @@ def load():
         "iqsb_collapse": [c_vp, c_uint, c_int],
         "iqsb_axpy": [c_vp, c_vp, c_vp],
         "iqsb_permute_local": [c_vp, c_vp, c_uint],
+        "iqsb_plan_permute": [c_vp, c_uint, c_vp, c_int, ctypes.POINTER(c_int)],
         "iqsb_plan_global": [c_int, c_int, c_int, c_uint, c_uint, c_uint, c_vp],
         "iqsb_share": [c_vp],
         "iqsb_idle_global": [c_vp],

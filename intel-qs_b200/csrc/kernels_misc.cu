@@ -3,7 +3,10 @@
 // Reference loops replaced:
 //   Initialize("base"/"++++")  src/qureg_init.cpp:238-244, 335-347; qureg_utils.cpp:173-184
 //   AmplitudeWiseSum           src/qureg_utils.cpp:199-226
-//   PermuteLocalQubits         src/qureg_permute.cpp:90-100 (out-of-place bit permutation)
+//   PermuteLocalQubits         src/qureg_permute.cpp:90-100 (there: a full copy + per-amplitude scatter;
+//                              here: a few in-place tile phases through shared memory)
+#include <stdlib.h>
+
 #include "iqsb_internal.cuh"
 
 namespace {
@@ -55,37 +58,142 @@ __global__ void __launch_bounds__(kBlock)
   }
 }
 
-// Bit permutation, gather form: dst[j] = src[pext-like(j)].  src_bit[b] = which bit of the
-// SOURCE index supplies bit b of the destination index... we need the inverse: for output j,
-// source i has bit sb = bit dst_of[sb] of j.  The table `src_from[b]` gives, for source bit b,
-// the destination bit that holds it.  Bits below `keep` are untouched (identity), so a thread
-// moves a contiguous run of 2^keep amplitudes when keep >= 1.
-struct PermTable {
-  uint8_t dst_bit[64];
+// Local qubit permutation by in-place TILE phases.
+// A phase permutes the amplitudes inside tiles: a tile is the set of 2^nS amplitudes whose indices
+// differ only in the nS bit positions pos[0] < pos[1] < ... (all other bits fixed), and the phase
+// applies one bit permutation sigma of those positions.  Because sigma leaves the other bits alone,
+// a tile maps onto itself: the CTA loads it, scatters it through shared memory (slot t -> slot
+// sigma(t)) and writes it back to the same addresses -- in place, one read and one write of HBM per
+// phase, no scratch shard.  The lowest positions are always part of the tile, so global accesses are
+// contiguous runs of 2^kRun amplitudes.  An arbitrary permutation of the M local qubits is split by
+// the host into a few such phases (plan_phases below).
+constexpr int kTileMax = 12;   // tile exponent (64 KiB of ComplexDP)
+constexpr int kRun = 4;        // low positions always in the tile: 256-byte runs for ComplexDP
+
+struct TilePhase {
+  uint8_t pos[kTileMax];      // ascending positions forming the tile
+  uint8_t dstslot[kTileMax];  // tile-local bit k moves to tile-local bit dstslot[k]
+  int nS;
 };
 
-template <typename T>
-__global__ void __launch_bounds__(kBlock)
-    k_permute_gather_w2(const Chunk<T> *__restrict__ src, Chunk<T> *__restrict__ dst, uint64_t nchunks,
-                        unsigned nbits, PermTable tab) {
-  // chunk index c covers amplitude bits 1..nbits-1; bit 0 is fixed (dst_bit[0] == 0).
-  const uint64_t stride = (uint64_t)gridDim.x * kBlock;
-  for (uint64_t j = (uint64_t)blockIdx.x * kBlock + threadIdx.x; j < nchunks; j += stride) {
-    uint64_t i = 0;
-    for (unsigned b = 1; b < nbits; ++b) i |= ((j >> (tab.dst_bit[b] - 1)) & 1ull) << (b - 1);
-    st_chunk(dst + j, ld_chunk(src + i));
+template <typename T, int kPermThreads>
+__global__ void __launch_bounds__(kPermThreads) k_permute_tile(Cx<T> *__restrict__ state, uint64_t nouter, TilePhase ph) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cx<T> *tile = reinterpret_cast<Cx<T> *>(smem_raw);
+  // offset tables: global offset and destination slot of tile-local index t = lo | hi << 8
+  __shared__ uint64_t g_lo[256], g_hi[16];
+  __shared__ uint16_t l_lo[256], l_hi[16];
+  const int nS = ph.nS;
+  for (unsigned t = threadIdx.x; t < 256 + 16; t += kPermThreads) {
+    unsigned v = t < 256 ? t : (t - 256) << 8;
+    uint64_t go = 0;
+    unsigned lo = 0;
+    for (int k = 0; k < nS; ++k)
+      if ((v >> k) & 1u) { go |= 1ull << ph.pos[k]; lo |= 1u << ph.dstslot[k]; }
+    if (t < 256) { g_lo[t] = go; l_lo[t] = (uint16_t)lo; }
+    else { g_hi[t - 256] = go; l_hi[t - 256] = (uint16_t)lo; }
+  }
+  __syncthreads();
+  const unsigned tsize = 1u << nS;
+  constexpr int U = 2048 / kPermThreads;  // independent 16-byte loads in flight per thread
+  for (uint64_t o = blockIdx.x; o < nouter; o += gridDim.x) {
+    uint64_t base = o;
+    for (int k = 0; k < nS; ++k) base = insert_zero(base, ph.pos[k]);
+    for (unsigned t0 = threadIdx.x; t0 < tsize; t0 += kPermThreads * U) {
+      Cx<T> v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unsigned t = t0 + u * kPermThreads;
+        if (t < tsize) v[u] = ld_amp(state + (base | g_lo[t & 255] | g_hi[t >> 8]));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unsigned t = t0 + u * kPermThreads;
+        if (t < tsize) tile[l_lo[t & 255] | l_hi[t >> 8]] = v[u];
+      }
+    }
+    __syncthreads();
+    for (unsigned t0 = threadIdx.x; t0 < tsize; t0 += kPermThreads * U) {
+      Cx<T> v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unsigned t = t0 + u * kPermThreads;
+        if (t < tsize) v[u] = tile[t];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unsigned t = t0 + u * kPermThreads;
+        if (t < tsize) st_amp(state + (base | g_lo[t & 255] | g_hi[t >> 8]), v[u]);
+      }
+    }
+    __syncthreads();
   }
 }
-template <typename T>
-__global__ void __launch_bounds__(kBlock)
-    k_permute_gather_w1(const Cx<T> *__restrict__ src, Cx<T> *__restrict__ dst, uint64_t n, unsigned nbits,
-                        PermTable tab) {
-  const uint64_t stride = (uint64_t)gridDim.x * kBlock;
-  for (uint64_t j = (uint64_t)blockIdx.x * kBlock + threadIdx.x; j < n; j += stride) {
-    uint64_t i = 0;
-    for (unsigned b = 0; b < nbits; ++b) i |= ((j >> tab.dst_bit[b]) & 1ull) << b;
-    st_amp(dst + j, ld_amp(src + i));
+
+// Split "content of position b goes to position dst[b]" into tile phases.
+static int plan_phases(const uint8_t *dst, unsigned nbits, TilePhase *out, int max_phases) {
+  uint8_t cur[64];
+  for (unsigned b = 0; b < nbits; ++b) cur[b] = dst[b];
+  const unsigned K = nbits < (unsigned)kTileMax ? nbits : (unsigned)kTileMax;
+  const unsigned run = nbits < (unsigned)kRun ? nbits : (unsigned)kRun;
+  int nph = 0;
+  for (;;) {
+    bool todo = false;
+    for (unsigned b = 0; b < nbits; ++b) todo = todo || cur[b] != b;
+    if (!todo) break;
+    if (nph == max_phases) return -1;
+    bool in[64] = {false};
+    unsigned cnt = 0;
+    for (unsigned b = 0; b < run; ++b) { in[b] = true; ++cnt; }
+    // pull in chains b -> cur[b] -> ... : first those that start inside the tile, then the others
+    for (int pass = 0; pass < 2; ++pass)
+      for (unsigned s0 = 0; s0 < nbits && cnt < K; ++s0) {
+        if (cur[s0] == s0 || (pass == 0 && !in[s0])) continue;
+        if (!in[s0] && K - cnt < 2) continue;  // a lone new bit cannot be finalised
+        unsigned b = s0;
+        do {
+          if (!in[b]) { in[b] = true; ++cnt; }
+          b = cur[b];
+        } while (cnt < K && (!in[b] || (b != s0 && cur[b] != b && !in[cur[b]])));
+      }
+    // a full-size tile keeps every CTA busy: pad with the lowest positions not used yet (they stay put)
+    for (unsigned b = 0; b < nbits && cnt < K; ++b)
+      if (!in[b]) { in[b] = true; ++cnt; }
+    // sigma on the tile: honour every destination that lies inside, park the rest on the free slots
+    uint8_t sigma[64];
+    bool used[64] = {false}, placed[64] = {false};
+    for (unsigned b = 0; b < nbits; ++b)
+      if (in[b] && in[cur[b]]) { sigma[b] = cur[b]; used[cur[b]] = true; placed[b] = true; }
+    for (unsigned b = 0; b < nbits; ++b)  // stay in place when possible
+      if (in[b] && !placed[b] && !used[b]) { sigma[b] = (uint8_t)b; used[b] = true; placed[b] = true; }
+    for (unsigned b = 0, f = 0; b < nbits; ++b)
+      if (in[b] && !placed[b]) {
+        while (!in[f] || used[f]) ++f;
+        sigma[b] = (uint8_t)f;
+        used[f] = true;
+        placed[b] = true;
+      }
+    // emit
+    TilePhase &ph = out[nph++];
+    ph.nS = 0;
+    int slot_of[64];
+    for (unsigned b = 0; b < nbits; ++b)
+      if (in[b]) { slot_of[b] = ph.nS; ph.pos[ph.nS++] = (uint8_t)b; }
+    for (int k = 0; k < ph.nS; ++k) ph.dstslot[k] = (uint8_t)slot_of[sigma[ph.pos[k]]];
+    for (int k = ph.nS; k < kTileMax; ++k) ph.pos[k] = ph.dstslot[k] = 0;
+    // the content that sat at b is now at sigma[b]
+    uint8_t nxt[64];
+    for (unsigned b = 0; b < nbits; ++b) nxt[b] = cur[b];
+    for (unsigned b = 0; b < nbits; ++b)
+      if (in[b]) nxt[sigma[b]] = cur[b];
+    bool progress = false;
+    for (unsigned b = 0; b < nbits; ++b) {
+      progress = progress || (nxt[b] == b && cur[b] != b);
+      cur[b] = nxt[b];
+    }
+    if (!progress) return -1;
   }
+  return nph;
 }
 
 inline int stream_grid(const iqsb_ctx *ctx, uint64_t nwork) {
@@ -144,80 +252,68 @@ extern "C" int iqsb_axpy(iqsb_state *a, const iqsb_state *b, const double f[2]) 
   return iqsb_check_launch(ctx, "k_axpy");
 }
 
+// Pure host function (no GPU needed): the tile phases iqsb_permute_local would run.
+// out[p*25 + 0] = nS, out[p*25 + 1 .. 12] = pos[], out[p*25 + 13 .. 24] = dstslot[].
+extern "C" int iqsb_plan_permute(const uint8_t *dst_bit, unsigned nbits, uint8_t *out, int max_phases, int *nphases) {
+  IQSB_REQUIRE(dst_bit && out && nphases && nbits <= 63 && max_phases > 0 && max_phases <= 64, "iqsb_plan_permute: bad argument");
+  TilePhase phases[64];
+  int nph = plan_phases(dst_bit, nbits, phases, max_phases);
+  IQSB_REQUIRE(nph >= 0, "iqsb_plan_permute: planning failed");
+  for (int p = 0; p < nph; ++p) {
+    out[p * 25] = (uint8_t)phases[p].nS;
+    for (int k = 0; k < kTileMax; ++k) {
+      out[p * 25 + 1 + k] = phases[p].pos[k];
+      out[p * 25 + 13 + k] = phases[p].dstslot[k];
+    }
+  }
+  *nphases = nph;
+  return IQSB_OK;
+}
+
 // new[j] = old[i], bit b of i -> bit dst_bit[b] of j.
 extern "C" int iqsb_permute_local(iqsb_state *st, const uint8_t *dst_bit, unsigned nbits) {
   IQSB_REQUIRE(st && dst_bit, "iqsb_permute_local: null argument");
   IQSB_REQUIRE(nbits == st->log2_local, "iqsb_permute_local: nbits must equal log2(local_amps)");
   uint64_t seen = 0;
   bool identity = true;
-  PermTable tab;
-  for (unsigned b = 0; b < 64; ++b) tab.dst_bit[b] = (uint8_t)b;
+  IQSB_REQUIRE(nbits <= 63, "iqsb_permute_local: too many bits");
   for (unsigned b = 0; b < nbits; ++b) {
     IQSB_REQUIRE(dst_bit[b] < nbits && !((seen >> dst_bit[b]) & 1), "iqsb_permute_local: not a permutation");
     seen |= 1ull << dst_bit[b];
-    tab.dst_bit[b] = dst_bit[b];
     identity = identity && dst_bit[b] == b;
   }
   if (identity) return IQSB_OK;
   iqsb_ctx *ctx = st->ctx;
-  size_t bytes = st->local_amps * st->amp_bytes();
-  // A bit permutation is a product of (nbits - #cycles) transpositions, and a transposition is a
-  // SWAP sweep that moves half of the shard in place (16*L bytes, no scratch).  The out-of-place
-  // gather below costs a read of scattered 16/32-byte pieces plus two more passes for the copy back
-  // and needs a second shard of HBM; measured at 2^32 amplitudes a full bit reversal takes 250 ms that
-  // way against ~10 ms per transposition.  So: transpositions unless there are very many of them.
-  unsigned transpositions = 0;
-  {
-    uint64_t visited = 0;
-    for (unsigned b = 0; b < nbits; ++b) {
-      if ((visited >> b) & 1) continue;
-      unsigned len = 0;
-      for (unsigned c = b; !((visited >> c) & 1); c = dst_bit[c]) { visited |= 1ull << c; ++len; }
-      transpositions += len - 1;
+  TilePhase phases[64];
+  int nph = plan_phases(dst_bit, nbits, phases, 64);
+  IQSB_REQUIRE(nph >= 0, "iqsb_permute_local: internal error while planning the tile phases");
+  static int threads = 0;
+  if (!threads) {
+    const char *e = getenv("IQSB_PERM_THREADS");
+    threads = e ? atoi(e) : 512;
+    if (threads != 256 && threads != 512 && threads != 1024) threads = 512;
+  }
+  for (int p = 0; p < nph; ++p) {
+    const TilePhase &ph = phases[p];
+    size_t smem = st->amp_bytes() << ph.nS;
+    uint64_t nouter = st->local_amps >> ph.nS;
+#define IQSB_PERM_LAUNCH(T, TH)                                                                                        \
+  {                                                                                                                    \
+    int per_sm = 1;                                                                                                    \
+    IQSB_CUDA(cudaFuncSetAttribute(k_permute_tile<T, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    IQSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_permute_tile<T, TH>, TH, smem));                \
+    if (per_sm < 1) per_sm = 1;                                                                                        \
+    uint64_t cap = (uint64_t)ctx->num_sms * per_sm;                                                                    \
+    unsigned grid = (unsigned)(nouter < cap ? nouter : cap);                                                           \
+    k_permute_tile<T, TH><<<grid, TH, smem, ctx->stream>>>((Cx<T> *)st->d, nouter, ph);                                \
+  }
+    if (st->dtype == IQSB_F64) {
+      if (threads == 256) IQSB_PERM_LAUNCH(double, 256) else if (threads == 1024) IQSB_PERM_LAUNCH(double, 1024) else IQSB_PERM_LAUNCH(double, 512)
+    } else {
+      if (threads == 256) IQSB_PERM_LAUNCH(float, 256) else if (threads == 1024) IQSB_PERM_LAUNCH(float, 1024) else IQSB_PERM_LAUNCH(float, 512)
     }
+#undef IQSB_PERM_LAUNCH
+    IQSB_TRY(iqsb_check_launch(ctx, "k_permute_tile"));
   }
-  void *scratch = nullptr;
-  cudaError_t e = transpositions <= 24 ? cudaErrorMemoryAllocation : cudaMalloc(&scratch, bytes);
-  if (e != cudaSuccess) {
-    (void)cudaGetLastError();
-    uint8_t cur[64];  // cur[b] = destination still owed by the data sitting at source bit b
-    for (unsigned b = 0; b < nbits; ++b) cur[b] = dst_bit[b];
-    const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
-    for (unsigned b = 0; b < nbits; ++b) {
-      while (cur[b] != b) {
-        unsigned t = cur[b];  // content of bit b must go to bit t: swap bits b and t
-        IQSB_TRY(iqsb_swap2x2(st, b < t ? b : t, b < t ? t : b, X));
-        uint8_t tmp = cur[t];
-        cur[t] = (uint8_t)t;  // bit t now holds its final content
-        cur[b] = tmp;
-      }
-    }
-    return IQSB_OK;
-  }
-  int rc = IQSB_OK;
-  if (dst_bit[0] == 0 && st->local_amps >= 2) {
-    uint64_t nchunks = st->local_amps / 2;
-    int grid = stream_grid(ctx, nchunks);
-    if (st->dtype == IQSB_F64)
-      k_permute_gather_w2<double><<<grid, kBlock, 0, ctx->stream>>>((const Chunk<double> *)st->d, (Chunk<double> *)scratch, nchunks, nbits, tab);
-    else
-      k_permute_gather_w2<float><<<grid, kBlock, 0, ctx->stream>>>((const Chunk<float> *)st->d, (Chunk<float> *)scratch, nchunks, nbits, tab);
-  } else {
-    int grid = stream_grid(ctx, st->local_amps);
-    if (st->dtype == IQSB_F64)
-      k_permute_gather_w1<double><<<grid, kBlock, 0, ctx->stream>>>((const Cx<double> *)st->d, (Cx<double> *)scratch, st->local_amps, nbits, tab);
-    else
-      k_permute_gather_w1<float><<<grid, kBlock, 0, ctx->stream>>>((const Cx<float> *)st->d, (Cx<float> *)scratch, st->local_amps, nbits, tab);
-  }
-  rc = iqsb_check_launch(ctx, "k_permute_gather");
-  if (rc == IQSB_OK) {
-    cudaError_t e2 = cudaMemcpyAsync(st->d, scratch, bytes, cudaMemcpyDeviceToDevice, ctx->stream);
-    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
-    if (e2 != cudaSuccess) {
-      iqsb_set_error("iqsb_permute_local: copy back failed: %s", cudaGetErrorString(e2));
-      rc = IQSB_ERR_CUDA;
-    }
-  }
-  cudaFree(scratch);
-  return rc;
+  return IQSB_OK;
 }

@@ -173,6 +173,21 @@ int iqsb_collapse(iqsb_state *st, unsigned pos, int value);
 /* a[i] += f * b[i]: AmplitudeWiseSum (src/qureg_utils.cpp:199-226) */
 int iqsb_axpy(iqsb_state *a, const iqsb_state *b, const double f[2]);
 
+/* ---- QAOA helpers (src/qaoa_features.cpp): a classical cost function lives in Re(diag[i]) -------- */
+/* diag[i] = cut value of the bit string of global index glb_start + i (program order via
+ * pos_of_qubit[q] = data position of program qubit q); adjacency is nverts x nverts, row-major.
+ * weighted == 0: integer arithmetic of InitializeVectorAsMaxCutCostFunction (:58-118);
+ * weighted != 0: the floating-point loop of InitializeVectorAsWeightedMaxCutCostFunction (:121-203),
+ * same operation order.  Returns the largest local cut. */
+int iqsb_qaoa_maxcut(iqsb_state *diag, unsigned nverts, const double *adjacency, int weighted, const uint8_t *pos_of_qubit,
+                     uint64_t glb_start, double *max_cut_local);
+/* psi[i] *= exp(-i gamma Re diag[i]): ImplementQaoaLayerBasedOnCostFunction (:255-266) */
+int iqsb_qaoa_layer(iqsb_state *psi, const iqsb_state *diag, double gamma);
+/* out[0] = sum Re diag |psi|^2, out[1] = sum (Re diag)^2 |psi|^2 (local): GetExpectationValue[Squared]FromCostFunction (:277-335) */
+int iqsb_qaoa_expect(iqsb_state *psi, const iqsb_state *diag, double out[2]);
+/* out[floor(Re diag / bin_width + eps)] += |psi|^2 (local): the three GetHistogramFromCostFunction* (:345-523) */
+int iqsb_qaoa_histogram(iqsb_state *psi, const iqsb_state *diag, int nbins, double bin_width, double eps, double *out);
+
 /* ---- qubit reordering: PermuteLocalQubits (src/qureg_permute.cpp:55-104) ------------- */
 /* new[j] = old[i] where bit b of i becomes bit dst_bit[b] of j, b < log2(local_amps). */
 int iqsb_permute_local(iqsb_state *st, const uint8_t *dst_bit, unsigned nbits);

@@ -113,6 +113,10 @@ def load():
         "iqsb_entropy_stats": [c_vp, c_vp],
         "iqsb_collapse": [c_vp, c_uint, c_int],
         "iqsb_axpy": [c_vp, c_vp, c_vp],
+        "iqsb_qaoa_maxcut": [c_vp, c_uint, c_vp, c_int, c_vp, c_u64, ctypes.POINTER(c_dbl)],
+        "iqsb_qaoa_layer": [c_vp, c_vp, c_dbl],
+        "iqsb_qaoa_expect": [c_vp, c_vp, c_vp],
+        "iqsb_qaoa_histogram": [c_vp, c_vp, c_int, c_dbl, c_dbl, c_vp],
         "iqsb_permute_local": [c_vp, c_vp, c_uint],
         "iqsb_plan_permute": [c_vp, c_uint, c_vp, c_int, ctypes.POINTER(c_int)],
         "iqsb_plan_global": [c_int, c_int, c_int, c_uint, c_uint, c_uint, c_vp],
@@ -367,6 +371,28 @@ class State:
     def axpy(self, other, f=1.0):
         ff = _c2(f)
         _chk(self.L.iqsb_axpy(self.h, other.h, ff.ctypes.data_as(c_vp)))
+
+    # QAOA helpers (this shard is the cost-function vector `diag` or the state `psi`)
+    def qaoa_maxcut(self, adjacency, weighted=False, pos_of_qubit=None, glb_start=0):
+        a = np.ascontiguousarray(adjacency, dtype=np.float64)
+        n = a.shape[0]
+        pos = np.ascontiguousarray(range(n) if pos_of_qubit is None else pos_of_qubit, dtype=np.uint8)
+        o = c_dbl()
+        _chk(self.L.iqsb_qaoa_maxcut(self.h, n, a.ctypes.data_as(c_vp), int(bool(weighted)), pos.ctypes.data_as(c_vp), glb_start, ctypes.byref(o)))
+        return o.value
+
+    def qaoa_layer(self, diag, gamma):
+        _chk(self.L.iqsb_qaoa_layer(self.h, diag.h, gamma))
+
+    def qaoa_expect(self, diag):
+        o = np.zeros(2)
+        _chk(self.L.iqsb_qaoa_expect(self.h, diag.h, o.ctypes.data_as(c_vp)))
+        return float(o[0]), float(o[1])
+
+    def qaoa_histogram(self, diag, nbins, bin_width=1.0, eps=0.0):
+        o = np.zeros(nbins)
+        _chk(self.L.iqsb_qaoa_histogram(self.h, diag.h, nbins, bin_width, eps, o.ctypes.data_as(c_vp)))
+        return o
 
     def permute_local(self, dst_bit):
         a = np.ascontiguousarray(dst_bit, dtype=np.uint8)

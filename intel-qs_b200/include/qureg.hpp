@@ -243,6 +243,12 @@ class QubitRegister {
   void SyncToHost();
   // device handle of the shard (C ABI, include/iqsb.h)
   iqsb_state *DeviceState() { return dev_; }
+  // make the device copy current: flush pending fused gates and write back host-side edits
+  void PrepareDevice() const {
+    const_cast<QubitRegister *>(this)->FlushForRead();
+    BeforeDeviceOp();
+  }
+  iqsb_state *DeviceState() const { return dev_; }
 
   // Members (public in the reference)
   std::size_t num_qubits;

@@ -4,8 +4,7 @@
 // pybind11/intelqs_py.cpp:56-426: EnvInit/EnvFinalize, QubitRegister with the NumPy buffer
 // protocol, named gates, custom 2x2 gates from a complex128 array, measurement, expectation
 // values, RandomNumberGenerator, MPIEnvironment statics), so notebooks and scripts written for
-// Intel-QS run unchanged.  Channels (CM4x4 / CM16x16) and the QAOA helpers are outside the B200
-// scope and are not bound.  Additions (marked "B200") expose what the reference's module lacks.
+// Intel-QS run unchanged.  Channels (CM4x4 / CM16x16) are outside the B200 scope and are not bound.  Additions (marked "B200") expose what the reference's module lacks.
 #include <pybind11/complex.h>
 #include <pybind11/iostream.h>
 #include <pybind11/numpy.h>
@@ -16,6 +15,7 @@
 #include <vector>
 
 #include "iqsb.h"
+#include "qaoa_features.hpp"
 #include "qureg.hpp"
 
 namespace py = pybind11;
@@ -223,6 +223,22 @@ PYBIND11_MODULE(intelqs_py, m) {
         if (iqsb_download(a.DeviceState(), out.mutable_data(), 0, a.LocalSize()) != IQSB_OK) throw std::runtime_error(iqsb_last_error());
         return out;
       }, "B200: copy of the local shard as a complex128 array (one device-to-host copy)");
+
+  // QAOA helpers (reference pybind11/intelqs_py.cpp:362-393): the loops run on the device
+  m.def("InitializeVectorAsMaxCutCostFunction", &iqs::qaoa::InitializeVectorAsMaxCutCostFunction<ComplexDP>,
+        "Use IQS vector to store a large real vector and not as a quantum state.");
+  m.def("InitializeVectorAsWeightedMaxCutCostFunction", &iqs::qaoa::InitializeVectorAsWeightedMaxCutCostFunction<ComplexDP>,
+        "Use IQS vector to store a large real vector and not as a quantum state.");
+  m.def("ImplementQaoaLayerBasedOnCostFunction", &iqs::qaoa::ImplementQaoaLayerBasedOnCostFunction<ComplexDP>, "Implement exp(-i gamma C)|psi>.");
+  m.def("GetExpectationValueFromCostFunction", &iqs::qaoa::GetExpectationValueFromCostFunction<ComplexDP>,
+        "Get expectation value from the cost function.");
+  m.def("GetExpectationValueSquaredFromCostFunction", &iqs::qaoa::GetExpectationValueSquaredFromCostFunction<ComplexDP>,
+        "Get expectation value squared from the cost function.");
+  m.def("GetHistogramFromCostFunction", &iqs::qaoa::GetHistogramFromCostFunction<ComplexDP>, "Get histogram instead of just the expectation value.");
+  m.def("GetHistogramFromCostFunctionWithWeightsRounded", &iqs::qaoa::GetHistogramFromCostFunctionWithWeightsRounded<ComplexDP>,
+        "Get histogram instead of just the expectation value for a weighted graph, with all cut values rounded down.");
+  m.def("GetHistogramFromCostFunctionWithWeightsBinned", &iqs::qaoa::GetHistogramFromCostFunctionWithWeightsBinned<ComplexDP>,
+        "Get histogram instead of just the expectation value for a weighted graph, with specified bin width.");
 
   py::class_<Environment>(m, "MPIEnvironment")
       .def(py::init<>())

@@ -28,6 +28,9 @@ if __name__ == "__main__":
     r = subprocess.run([os.path.join(BIN, "iqs_interface")], input=QASM, capture_output=True, text=True, env=env, timeout=600)
     open(os.path.join(HERE, "examples", "iqs_interface.txt"), "w").write(f"EXIT {r.returncode}\n" + r.stdout)
     print("iqs_interface exit", r.returncode)
+    r = subprocess.run([os.path.join(BIN, "qaoa_check")], capture_output=True, text=True, env=env, timeout=600)
+    open(os.path.join(HERE, "examples", "qaoa_check.txt"), "w").write(f"EXIT {r.returncode}\n" + r.stdout)
+    print("qaoa_check exit", r.returncode)
     for name, args in COMMANDS.items():
         r = subprocess.run([os.path.join(BIN, name)] + args, capture_output=True, text=True, env=env, timeout=600)
         # (benchgates ends with `return 1` also on success; the exit code is part of the fixture)

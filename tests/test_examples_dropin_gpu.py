@@ -116,3 +116,10 @@ def test_qasm_interface():
     """interface/src/*.cpp, the stdin QASM interpreter, relinked unchanged."""
     qasm = ".malloc 3\nH q0\nCNOT q0,q1\nT q1\nS q2\nX q2\nTdag q0\nMeasZ q0\nMeasZ q1\nMeasZ q2\n.version\n.free\n\n"
     compare("iqs_interface", [], stdin=qasm)
+
+
+def test_qaoa_features():
+    """iqs::qaoa::* (SURVEY.md 8f row 3): MaxCut cost vectors (integer and weighted, permuted qubit
+    order), QAOA layers, cost expectation values and the three histograms, against the reference's
+    own qaoa_features.cpp run on the CPU."""
+    compare("qaoa_check", [], tol=2e-12)

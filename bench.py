@@ -401,6 +401,24 @@ def gpu_arm(args, pkg):
                "h2d_bytes_per_step": int(64 * job_gates / args.steps), "d2h_bytes_per_step": 8,
                "gates_per_s": job_gates / t_e2e, "api": "intelqs_py.QubitRegister.Apply1QubitGate/ApplyControlled1QubitGate(numpy 2x2) + GetProbability",
                "note": "the state stays resident in HBM like the reference's stays in RAM; per-step host inputs are the gate matrices"}
+        # the same steps with gate fusion on (TurnOnFusion): reported next to the headline, not as it
+        try:
+            psi.TurnOnFusion(11)
+            api_layer(layers[0], cm[0])
+            iqs.MPIEnvironment.StateBarrier()
+            if world > 1:
+                dist.barrier()
+            iqs.DeviceTimerStart()
+            t0 = time.perf_counter()
+            for s in range(args.warmup, total):
+                api_layer(layers[s], cm[s])
+            ms_dev = iqs.DeviceTimerStop()
+            t_f = all_max(max(time.perf_counter() - t0, ms_dev * 1e-3))
+            psi.TurnOffFusion()
+            e2e["fused"] = {"value": job_bytes / t_f / 1e9, "unit": "GB/s", "gates_per_s": job_gates / t_f,
+                            "note": "TurnOnFusion(): runs of gates share one HBM sweep (shared-memory tiles built from arbitrary qubit positions)"}
+        except Exception as exc:
+            log(f"[bench] fused leg failed: {exc!r}")
         del psi
         iqs.EnvFinalize()
     except Exception as exc:  # the end-to-end leg must never hide the device-side number

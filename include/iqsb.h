@@ -135,14 +135,20 @@ int iqsb_gate2(iqsb_state *st, unsigned pos_high, unsigned pos_low, const double
 typedef struct iqsb_fgate {
   int32_t kind; /* 0 = 1-qubit gate on `target`; 1 = controlled gate (control, target) */
   int32_t control;
-  int32_t target; /* target position, must be < the tile exponent */
+  int32_t target; /* target position (local) */
   int32_t pad;
   double m[8];
 } iqsb_fgate;
-/* apply `ngates` gates in order in ONE sweep over HBM; every target must be < max tile
- * exponent (iqsb_fused_max_log2tile()), controls may be any local position. */
+/* Apply `ngates` gates in order with as few sweeps over HBM as possible.  Targets and controls may
+ * be ANY local positions: the batch is cut into runs of consecutive gates whose targets fit in one
+ * shared-memory tile (2^11 amplitudes = the 4 lowest positions + 7 positions chosen per run); each
+ * run costs one read and one write of the state. */
 int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates);
+/* tile exponent (11, or log2(local_amps) for tiny shards) */
 int iqsb_fused_max_log2tile(const iqsb_state *st);
+/* Pure host function: the runs iqsb_fused would execute.  run_end[r] = one past the last gate of
+ * run r; tiles[12 r] = number of tile positions, tiles[12 r + 1 ..] = the positions (ascending). */
+int iqsb_plan_fused(const iqsb_fgate *gates, int ngates, unsigned log2_local, int *run_end, uint8_t *tiles, int max_runs, int *nruns);
 
 /* ---- reductions (warp-shuffle + fixed-order second stage; deterministic run to run) -- */
 /* sum |a|^2 over local amplitudes with bit pos == 1: GetProbability (src/qureg_measure.cpp:150-167) */

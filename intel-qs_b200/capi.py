@@ -24,6 +24,10 @@ class IqsbError(RuntimeError):
     pass
 
 
+class FGate(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("control", ctypes.c_int32), ("target", ctypes.c_int32), ("pad", ctypes.c_int32), ("m", c_dbl * 8)]
+
+
 class Plan(ctypes.Structure):
     _fields_ = [("active", ctypes.c_int32), ("partner", ctypes.c_int32), ("role", ctypes.c_int32), ("nfix", ctypes.c_int32),
                 ("pos", ctypes.c_uint32 * 3), ("val", ctypes.c_uint32 * 3), ("extra0", ctypes.c_uint64), ("extra1", ctypes.c_uint64),
@@ -37,6 +41,32 @@ def plan_global(kind, rank, nranks, M, pos1, pos2):
     return pl
 
 
+def _fgates(gates):
+    arr = (FGate * len(gates))()
+    for i, (kind, c, t, m) in enumerate(gates):
+        arr[i].kind, arr[i].control, arr[i].target = kind, c, t
+        mm = _m(m)
+        for k in range(8):
+            arr[i].m[k] = mm[k]
+    return arr
+
+
+def plan_fused(gates, log2_local):
+    """Host-only: [(first, last, tile positions)] runs that iqsb_fused executes for `gates`."""
+    arr = _fgates(gates)
+    n = len(gates)
+    run_end = (c_int * max(n, 1))()
+    tiles = np.zeros(12 * max(n, 1), dtype=np.uint8)
+    nruns = c_int()
+    _chk(load().iqsb_plan_fused(arr, n, log2_local, run_end, tiles.ctypes.data_as(c_vp), max(n, 1), ctypes.byref(nruns)))
+    out, first = [], 0
+    for r in range(nruns.value):
+        ns = int(tiles[12 * r])
+        out.append((first, int(run_end[r]), tiles[12 * r + 1 : 12 * r + 1 + ns].astype(int).tolist()))
+        first = int(run_end[r])
+    return out
+
+
 def plan_permute(dst_bit):
     """Host-only: list of (positions, dstslot) tile phases for a local qubit permutation."""
     a = np.ascontiguousarray(dst_bit, dtype=np.uint8)
@@ -48,10 +78,6 @@ def plan_permute(dst_bit):
         ns = int(out[25 * p])
         phases.append((out[25 * p + 1 : 25 * p + 1 + ns].astype(int).tolist(), out[25 * p + 13 : 25 * p + 13 + ns].astype(int).tolist()))
     return phases
-
-
-class FGate(ctypes.Structure):
-    _fields_ = [("kind", ctypes.c_int32), ("control", ctypes.c_int32), ("target", ctypes.c_int32), ("pad", ctypes.c_int32), ("m", c_dbl * 8)]
 
 
 def load():
@@ -102,6 +128,7 @@ def load():
         "iqsb_gate2": [c_vp, c_uint, c_uint, c_vp],
         "iqsb_fused": [c_vp, c_vp, c_int],
         "iqsb_fused_max_log2tile": [c_vp],
+        "iqsb_plan_fused": [c_vp, c_int, c_uint, c_vp, c_vp, c_int, ctypes.POINTER(c_int)],
         "iqsb_prob1": [c_vp, c_uint, ctypes.POINTER(c_dbl)],
         "iqsb_parity_expect": [c_vp, c_u64, c_u64, ctypes.POINTER(c_dbl)],
         "iqsb_norm2": [c_vp, ctypes.POINTER(c_dbl)],
@@ -307,13 +334,7 @@ class State:
 
     def fused(self, gates):
         """gates: list of (kind, control, target, m8)."""
-        arr = (FGate * len(gates))()
-        for i, (kind, c, t, m) in enumerate(gates):
-            arr[i].kind, arr[i].control, arr[i].target = kind, c, t
-            mm = _m(m)
-            for k in range(8):
-                arr[i].m[k] = mm[k]
-        _chk(self.L.iqsb_fused(self.h, arr, len(gates)))
+        _chk(self.L.iqsb_fused(self.h, _fgates(gates), len(gates)))
 
     def fused_max_log2tile(self):
         return int(self.L.iqsb_fused_max_log2tile(self.h))

@@ -1,69 +1,124 @@
-// kernels_fused.cu -- gate fusion: a batch of gates on low positions applied in ONE sweep
-// over HBM, the tile staged in shared memory.
+// kernels_fused.cu -- gate fusion: a batch of gates applied in as few sweeps over HBM as
+// possible, the amplitudes staged in shared-memory tiles.
 //
-// Replaces ApplyFusedGates (reference src/qureg_fusion.cpp:55-94), which replays the queued
-// gates block by block with blocks of 2^log2llc amplitudes sized for the CPU's last-level
-// cache.  Here the block is a shared-memory tile of 2^K amplitudes (K = 11: 32 KiB for
-// ComplexDP, several CTAs resident per SM so that the HBM traffic of one CTA overlaps the
-// shared-memory sweeps of the others).  Semantics are the reference's: targets must be below
-// the tile exponent; a control at or above it selects whole tiles
-// (src/qureg_applyctrl1qubitgate.cpp:296-309).
+// Replaces ApplyFusedGates (reference src/qureg_fusion.cpp:55-94), which replays the queued gates
+// block by block, with blocks of 2^log2llc CONTIGUOUS amplitudes sized for the CPU's last-level
+// cache -- so only gates whose target lies below log2llc can be fused there.
+//
+// Here a tile is the set of 2^K amplitudes (K = 11: 32 KiB of ComplexDP) whose indices differ only
+// in K chosen bit positions pos[0] < pos[1] < ...: the four lowest positions are always part of it
+// (global accesses are 256-byte runs, moved as 32-byte chunks), the other seven are whatever
+// positions the gates of the run act on.  A run of consecutive gates whose targets fit in one tile
+// costs ONE read and ONE write of the state, wherever the target qubits sit; iqsb_fused cuts a
+// batch into such runs greedily.  Controls may be anywhere: inside the tile they are a bit of the
+// tile-local index, outside they select whole tiles (the reference's rule for controls above the
+// block, src/qureg_applyctrl1qubitgate.cpp:296-309).
+//
+// Inside a tile every gate is one shared-memory round trip of the tile (16-byte slots, XOR-swizzled
+// so that the 8 lanes of a quarter-warp hit 8 different bank groups for every target slot).
+// Measured (profiles/): short runs are HBM-bound; beyond ~4 gates per run the shared-memory
+// bandwidth (~78 %) and the FP64 issue rate of the exact, non-contracted arithmetic (28 operations
+// per pair) bound the kernel at ~1.4 ms per gate for 2^30 amplitudes, 3.5x cheaper than a sweep.
+#include <string.h>
+
+#include <vector>
+
 #include "iqsb_internal.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxFusedGates = 4096;
+constexpr int kTile = 11;  // tile exponent
+constexpr int kLow = 4;    // lowest positions always in the tile
 
 template <typename T>
-struct FGate {
+struct alignas(16) FGate {
   Mat2<T> m;
-  int kind, control, target, pad;
+  int tslot;  // tile-local bit of the target
+  int ckind;  // 0: none, 1: control is tile-local bit `c`, 2: control is bit `c` of the global index (outside the tile)
+  int c;
+  int pad;
 };
 
-// 16-byte slots; XOR swizzle so that the 8 lanes of a quarter-warp hit 8 different bank
-// groups for every target position ("fused kernel").
+struct TileDesc {
+  uint8_t pos[kTile];
+  int nS;
+};
+
+// 16-byte slots; swizzle so that pairs (i, i + 2^s) are conflict free for every s
 __device__ __forceinline__ unsigned phys(unsigned i) { return i ^ (((i >> 3) & 1u) * 7u); }
 
 template <typename T>
+__device__ __forceinline__ FGate<T> load_gate(const FGate<T> *p) {
+  FGate<T> g;
+  const int4 *src = reinterpret_cast<const int4 *>(p);
+  int4 *dst = reinterpret_cast<int4 *>(&g);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(FGate<T>) / 16); ++i) dst[i] = __ldg(src + i);
+  return g;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    k_fused(Chunk<T> *__restrict__ state, uint64_t ntiles, unsigned K, const FGate<T> *__restrict__ gates, int ngates) {
+    k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, const FGate<T> *__restrict__ gates, int ngates) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cx<T> *tile = reinterpret_cast<Cx<T> *>(smem_raw);
-  const unsigned nchunks = 1u << (K - 1);
-  for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    Chunk<T> *g = state + (t << (K - 1));
-    const uint64_t base = t << K;
-    for (unsigned c = threadIdx.x; c < nchunks; c += kThreads) {
-      Chunk<T> v = ld_chunk(g + c);
-      tile[phys(2 * c)] = v.a;
-      tile[phys(2 * c + 1)] = v.b;
+  // chunk offset of tile-local chunk index c = lo | hi << 8 (c = tile-local amplitude index / 2)
+  __shared__ uint64_t g_lo[256], g_hi[4];
+  const int nS = td.nS;  // pos[0] == 0 always
+  for (unsigned t = threadIdx.x; t < 256 + 4; t += kThreads) {
+    unsigned v = t < 256 ? t : (t - 256) << 8;
+    uint64_t go = 0;
+    for (int k = 1; k < nS; ++k)
+      if ((v >> (k - 1)) & 1u) go |= 1ull << (td.pos[k] - 1);
+    if (t < 256) g_lo[t] = go;
+    else g_hi[t - 256] = go;
+  }
+  __syncthreads();
+  const unsigned nchunks = 1u << (nS - 1);
+  constexpr int U = 4;  // 32-byte loads in flight per thread
+  for (uint64_t o = blockIdx.x; o < nouter; o += gridDim.x) {
+    uint64_t base = o;  // amplitude index with zeros at the tile positions
+    for (int k = 0; k < nS; ++k) base = insert_zero(base, td.pos[k]);
+    Chunk<T> *g = state + (base >> 1);
+    for (unsigned c0 = threadIdx.x; c0 < nchunks; c0 += kThreads * U) {
+      Chunk<T> v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unsigned c = c0 + u * kThreads;
+        if (c < nchunks) v[u] = ld_chunk(g + (g_lo[c & 255] | g_hi[c >> 8]));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unsigned c = c0 + u * kThreads;
+        if (c < nchunks) {
+          tile[phys(2 * c)] = v[u].a;
+          tile[phys(2 * c + 1)] = v[u].b;
+        }
+      }
     }
     __syncthreads();
     for (int gi = 0; gi < ngates; ++gi) {
-      const FGate<T> G = gates[gi];
-      const unsigned tp = (unsigned)G.target;
-      bool controlled = G.kind == 1;
-      if (controlled && (unsigned)G.control >= K) {
-        if (!((base >> G.control) & 1ull)) continue;  // uniform over the CTA
-        controlled = false;
-      }
-      if (!controlled) {
-        const unsigned npairs = 1u << (K - 1);
+      const FGate<T> G = load_gate(gates + gi);
+      const unsigned ts = (unsigned)G.tslot;
+      if (G.ckind == 2 && !((base >> G.c) & 1ull)) continue;  // uniform over the CTA
+      if (G.ckind != 1) {
+        const unsigned npairs = 1u << (nS - 1);
         for (unsigned j = threadIdx.x; j < npairs; j += kThreads) {
-          unsigned i0 = (unsigned)insert_zero(j, tp), i1 = i0 | (1u << tp);
+          unsigned i0 = (unsigned)insert_zero(j, ts), i1 = i0 | (1u << ts);
           Cx<T> a = tile[phys(i0)], b = tile[phys(i1)];
           apply2x2(G.m, a, b);
           tile[phys(i0)] = a;
           tile[phys(i1)] = b;
         }
       } else {
-        const unsigned cp = (unsigned)G.control;
-        const unsigned lo = cp < tp ? cp : tp, hi = cp < tp ? tp : cp;
-        const unsigned npairs = 1u << (K - 2);
+        const unsigned cs = (unsigned)G.c;
+        const unsigned lo = cs < ts ? cs : ts, hi = cs < ts ? ts : cs;
+        const unsigned npairs = 1u << (nS - 2);
         for (unsigned j = threadIdx.x; j < npairs; j += kThreads) {
           unsigned x = (unsigned)insert_zero(insert_zero(j, lo), hi);
-          unsigned i0 = x | (1u << cp), i1 = i0 | (1u << tp);
+          unsigned i0 = x | (1u << cs), i1 = i0 | (1u << ts);
           Cx<T> a = tile[phys(i0)], b = tile[phys(i1)];
           apply2x2(G.m, a, b);
           tile[phys(i0)] = a;
@@ -72,45 +127,65 @@ __global__ void __launch_bounds__(kThreads)
       }
       __syncthreads();
     }
-    for (unsigned c = threadIdx.x; c < nchunks; c += kThreads) {
-      Chunk<T> v;
-      v.a = tile[phys(2 * c)];
-      v.b = tile[phys(2 * c + 1)];
-      st_chunk(g + c, v);
+    for (unsigned c0 = threadIdx.x; c0 < nchunks; c0 += kThreads * U) {
+      Chunk<T> v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unsigned c = c0 + u * kThreads;
+        if (c < nchunks) {
+          v[u].a = tile[phys(2 * c)];
+          v[u].b = tile[phys(2 * c + 1)];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        unsigned c = c0 + u * kThreads;
+        if (c < nchunks) st_chunk(g + (g_lo[c & 255] | g_hi[c >> 8]), v[u]);
+      }
     }
     __syncthreads();
   }
 }
 
+// one run: gates [first, last) of `in` all have their target in the tile `td`
 template <typename T>
-int run_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates, unsigned K) {
+int launch_run(iqsb_state *st, const iqsb_fgate *in, int first, int last, const TileDesc &td) {
   iqsb_ctx *ctx = st->ctx;
-  FGate<T> *h = new FGate<T>[ngates];
-  for (int i = 0; i < ngates; ++i) {
-    h[i].m = make_mat<T>(gates[i].m);
-    h[i].kind = gates[i].kind;
-    h[i].control = gates[i].control;
-    h[i].target = gates[i].target;
-    h[i].pad = 0;
+  int slot_of[64];
+  for (int p = 0; p < 64; ++p) slot_of[p] = -1;
+  for (int k = 0; k < td.nS; ++k) slot_of[td.pos[k]] = k;
+  std::vector<FGate<T>> gates((size_t)(last - first));
+  for (int k = first; k < last; ++k) {
+    FGate<T> &o = gates[k - first];
+    o.m = make_mat<T>(in[k].m);
+    o.tslot = slot_of[in[k].target];
+    o.pad = 0;
+    o.ckind = 0;
+    o.c = 0;
+    if (in[k].kind == 1) {
+      int c = in[k].control;
+      if (slot_of[c] >= 0) { o.ckind = 1; o.c = slot_of[c]; }
+      else { o.ckind = 2; o.c = c; }
+    }
   }
   FGate<T> *d = nullptr;
-  cudaError_t e = cudaMallocAsync((void **)&d, sizeof(FGate<T>) * ngates, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d, h, sizeof(FGate<T>) * ngates, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // h is pageable: copy is done after this
-  delete[] h;
+  size_t bytes = sizeof(FGate<T>) * gates.size();
+  cudaError_t e = cudaMallocAsync((void **)&d, bytes, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d, gates.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `gates` is pageable
   if (e != cudaSuccess) {
     iqsb_set_error("iqsb_fused: staging the gate list failed: %s", cudaGetErrorString(e));
     return IQSB_ERR_CUDA;
   }
-  size_t smem = (size_t)sizeof(Cx<T>) << K;
+  size_t smem = (size_t)sizeof(Cx<T>) << td.nS;
   IQSB_CUDA(cudaFuncSetAttribute(k_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   IQSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<T>, kThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  uint64_t ntiles = st->local_amps >> K;
+  uint64_t nouter = st->local_amps >> td.nS;
   uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
-  unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
-  k_fused<T><<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, ntiles, K, d, ngates);
+  unsigned grid = (unsigned)(nouter < cap ? nouter : cap);
+  k_fused<T><<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, (int)gates.size());
   int rc = iqsb_check_launch(ctx, "k_fused");
   cudaFreeAsync(d, ctx->stream);
   return rc;
@@ -120,23 +195,82 @@ int run_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates, unsigned K) {
 
 extern "C" int iqsb_fused_max_log2tile(const iqsb_state *st) {
   if (!st) return 0;
-  int k = 11;
+  int k = kTile;
   if ((unsigned)k > st->log2_local) k = (int)st->log2_local;
   return k;
+}
+
+// Pure host function: how iqsb_fused cuts a batch into runs.  run_end[r] = index one past the last
+// gate of run r; tiles[r*12] = number of tile positions, tiles[r*12 + 1 ..] = the positions.
+extern "C" int iqsb_plan_fused(const iqsb_fgate *gates, int ngates, unsigned log2_local, int *run_end, uint8_t *tiles, int max_runs, int *nruns) {
+  IQSB_REQUIRE((gates || ngates == 0) && run_end && tiles && nruns && max_runs > 0, "iqsb_plan_fused: null argument");
+  const unsigned K = log2_local < (unsigned)kTile ? log2_local : (unsigned)kTile;
+  const unsigned low = log2_local < (unsigned)kLow ? log2_local : (unsigned)kLow;
+  int r = 0, first = 0;
+  while (first < ngates) {
+    IQSB_REQUIRE(r < max_runs, "iqsb_plan_fused: more than %d runs", max_runs);
+    bool in[64] = {false};
+    unsigned cnt = 0;
+    for (unsigned b = 0; b < low; ++b) { in[b] = true; ++cnt; }
+    int last = first;
+    for (; last < ngates; ++last) {
+      unsigned t = (unsigned)gates[last].target;
+      IQSB_REQUIRE(t < log2_local, "iqsb_fused: gate %d: target %u is not a local position", last, t);
+      if (!in[t]) {
+        if (cnt == K) break;
+        in[t] = true;
+        ++cnt;
+      }
+    }
+    // use the spare slots for controls of the run (cheaper inside the tile), then for low positions
+    for (int k = first; k < last && cnt < K; ++k)
+      if (gates[k].kind == 1 && (unsigned)gates[k].control < log2_local && !in[gates[k].control]) { in[gates[k].control] = true; ++cnt; }
+    for (unsigned b = 0; b < log2_local && cnt < K; ++b)
+      if (!in[b]) { in[b] = true; ++cnt; }
+    uint8_t *td = tiles + r * 12;
+    td[0] = (uint8_t)cnt;
+    int n = 0;
+    for (unsigned b = 0; b < log2_local; ++b)
+      if (in[b]) td[1 + n++] = (uint8_t)b;
+    for (; n < kTile; ++n) td[1 + n] = 0;
+    run_end[r++] = last;
+    first = last;
+  }
+  *nruns = r;
+  return IQSB_OK;
 }
 
 extern "C" int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates) {
   IQSB_REQUIRE(st && (gates || ngates == 0), "iqsb_fused: null argument");
   IQSB_REQUIRE(ngates >= 0 && ngates <= kMaxFusedGates, "iqsb_fused: at most %d gates per call", kMaxFusedGates);
   if (ngates == 0) return IQSB_OK;
-  unsigned K = (unsigned)iqsb_fused_max_log2tile(st);
-  IQSB_REQUIRE(K >= 2, "iqsb_fused: shard too small");
   for (int i = 0; i < ngates; ++i) {
     IQSB_REQUIRE(gates[i].kind == 0 || gates[i].kind == 1, "iqsb_fused: gate %d has bad kind", i);
-    IQSB_REQUIRE(gates[i].target >= 0 && (unsigned)gates[i].target < K, "iqsb_fused: gate %d target %d >= tile exponent %u", i, gates[i].target, K);
+    IQSB_REQUIRE(gates[i].target >= 0 && (unsigned)gates[i].target < st->log2_local, "iqsb_fused: gate %d: target %d is not a local position", i,
+                 gates[i].target);
     if (gates[i].kind == 1)
       IQSB_REQUIRE(gates[i].control >= 0 && (unsigned)gates[i].control < st->log2_local && gates[i].control != gates[i].target,
                    "iqsb_fused: gate %d has bad control", i);
   }
-  return st->dtype == IQSB_F64 ? run_fused<double>(st, gates, ngates, K) : run_fused<float>(st, gates, ngates, K);
+  if (st->log2_local < 2) {  // nothing to tile
+    for (int i = 0; i < ngates; ++i) {
+      if (gates[i].kind == 0) IQSB_TRY(iqsb_gate1(st, (unsigned)gates[i].target, gates[i].m, 0, st->local_amps));
+      else IQSB_TRY(iqsb_cgate1(st, (unsigned)gates[i].control, (unsigned)gates[i].target, gates[i].m, 0, st->local_amps));
+    }
+    return IQSB_OK;
+  }
+  std::vector<int> run_end((size_t)ngates);
+  std::vector<uint8_t> tiles((size_t)ngates * 12);
+  int nruns = 0;
+  IQSB_TRY(iqsb_plan_fused(gates, ngates, st->log2_local, run_end.data(), tiles.data(), ngates, &nruns));
+  int first = 0;
+  for (int r = 0; r < nruns; ++r) {
+    TileDesc td;
+    td.nS = tiles[r * 12];
+    for (int k = 0; k < kTile; ++k) td.pos[k] = tiles[r * 12 + 1 + k];
+    int rc = st->dtype == IQSB_F64 ? launch_run<double>(st, gates, first, run_end[r], td) : launch_run<float>(st, gates, first, run_end[r], td);
+    if (rc != IQSB_OK) return rc;
+    first = run_end[r];
+  }
+  return IQSB_OK;
 }

@@ -16,7 +16,7 @@
 //     TurnOnSpecialize() (1q.cpp:213-219, ctrl.cpp:363-368, 383-391); here it is unconditional.
 //   * gates on global qubits run as one peer-memory kernel per rank (csrc/comm.cu), not as
 //     Sendrecv / Loop_SN / Sendrecv phases.
-//   * fusion batches are limited to targets below the shared-memory tile exponent; the queue and
+//   * fusion queues every gate with a local target (tiles are built from arbitrary positions); the
 //     flush rules are the reference's, plus a flush before every read of the state.
 #include "qureg_impl.hpp"
 
@@ -120,6 +120,7 @@ void QubitRegister<Type>::Apply1QubitGate(unsigned qubit, TM2x2<Type> const &m, 
   assert(position < num_qubits);
   if (fusion == true) {
     if (position < log2llc) {
+      if (fwindow.size() >= 4000) ApplyFusedGates();  // bound the window
       fwindow.push_back(std::make_tuple(std::string("sqg"), m, qubit, 0U));
       return;
     }
@@ -262,9 +263,9 @@ bool QubitRegister<Type>::ApplyControlled1QubitGate_helper(unsigned control_qubi
   bool full = (sind == 0 && eind == LocalSize());
 
   if (C < M && T < M) {
-    if (C > T && C >= log2llc && LocalSize() > (eind - sind)) {
-      // replay over a sub-block that lies entirely inside one value of the control bit
-      // (reference ctrl.cpp:296-309)
+    if (C > T && LocalSize() > (eind - sind) && (eind - sind) <= (UL(1) << C)) {
+      // a sub-block that lies entirely inside one value of the control bit: plain gate or nothing
+      // (the reference takes this branch for C >= log2llc, ctrl.cpp:296-309)
       if (check_bit(sind, C) == 1) {
         Check(iqsb_gate1(dev_, (unsigned)T, mm, sind, eind), "controlled gate (block form)");
         bytes = 2.0 * sizeof(Type) * double(eind - sind);
@@ -340,6 +341,7 @@ void QubitRegister<Type>::ApplyControlled1QubitGate(unsigned control_qubit, unsi
     unsigned target_position = (*qubit_permutation)[target_qubit];
     assert(target_position < num_qubits);
     if (target_position < log2llc) {
+      if (fwindow.size() >= 4000) ApplyFusedGates();  // bound the window
       fwindow.push_back(std::make_tuple(std::string("cqg"), m, control_qubit, target_qubit));
       return;
     }
@@ -600,12 +602,12 @@ void QubitRegister<Type>::TurnOnFusion(unsigned log2llc_) {
     if (!myrank) printf("Fusion is not enabled: num_qubits (%lu) is too small\n", num_qubits);
     fusion = false;
   } else {
-    // The reference sizes the block for the CPU's last-level cache (default 2^20 amplitudes).  Here
-    // the block is a shared-memory tile: gates whose target lies above the tile exponent are applied
-    // directly, exactly as the reference treats targets >= log2llc.
-    unsigned tile = (unsigned)iqsb_fused_max_log2tile(dev_);
-    this->log2llc = log2llc_ < tile ? log2llc_ : tile;
-    if (!myrank) printf("Fusion is enabled: log2llc = %u (requested %u) num_qubits = %lu\n", this->log2llc, log2llc_, num_qubits);
+    // The reference sizes a contiguous block for the CPU's last-level cache (default 2^20 amplitudes)
+    // and can only fuse gates whose target lies below log2llc.  The GPU engine builds its shared-memory
+    // tiles from arbitrary positions (csrc/kernels_fused.cu), so EVERY gate with a local target is
+    // queued; `log2llc` only keeps its role of switching fusion on.
+    this->log2llc = M;
+    if (!myrank) printf("Fusion is enabled: log2llc = %u (requested %u; every local target is fused) num_qubits = %lu\n", this->log2llc, log2llc_, num_qubits);
     fusion = true;
   }
 }

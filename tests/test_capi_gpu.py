@@ -313,32 +313,38 @@ def test_permute_local_bit_exact(gpu_ctx):
 
 
 def test_fused_matches_sequential(gpu_ctx, oracle):
-    n = 14
+    """Targets and controls anywhere: the batch is cut into tile runs, the result equals the
+    gate-by-gate oracle bit for bit."""
+    n = 16
     st = gpu_ctx.alloc(1 << n)
-    K = st.fused_max_log2tile()
-    assert K == 11
+    assert st.fused_max_log2tile() == 11
     psi = C.random_state(n, seed=21)
-    st.upload(psi)
-    ref = psi.copy()
     rng = np.random.Generator(np.random.MT19937(4))
-    gates = []
-    for i in range(60):
-        m = np.ascontiguousarray(random_unitary(rng)).ravel().view(np.float64).copy()
-        t = int(rng.integers(0, K))
-        if i % 3 == 0:
-            gates.append((0, 0, t, m))
-            oracle.gate1(ref, t, m)
-        else:
-            c = int(rng.integers(0, n))
-            while c == t:
+    for lo_only in (True, False):
+        st.upload(psi)
+        ref = psi.copy()
+        gates = []
+        for i in range(90):
+            m = np.ascontiguousarray(random_unitary(rng)).ravel().view(np.float64).copy()
+            t = int(rng.integers(0, 11 if lo_only else n))
+            if i % 3 == 0:
+                gates.append((0, 0, t, m))
+                oracle.gate1(ref, t, m)
+            else:
                 c = int(rng.integers(0, n))
-            gates.append((1, c, t, m))
-            oracle.cgate1(ref, c, t, m)
-    st.fused(gates)
-    got = st.download()
-    assert np.array_equal(got, ref), f"maxdiff={np.max(np.abs(got - ref))}"
+                while c == t:
+                    c = int(rng.integers(0, n))
+                gates.append((1, c, t, m))
+                oracle.cgate1(ref, c, t, m)
+        runs = capi.plan_fused(gates, n)
+        assert runs[0][0] == 0 and runs[-1][1] == len(gates)
+        if lo_only:
+            assert len(runs) == 1  # every target below the tile exponent: one sweep
+        st.fused(gates)
+        got = st.download()
+        assert np.array_equal(got, ref), f"maxdiff={np.max(np.abs(got - ref))}"
     with pytest.raises(capi.IqsbError):
-        st.fused([(0, 0, K, HM)])
+        st.fused([(0, 0, n, HM)])  # not a local position
     st.free()
 
 
@@ -426,7 +432,7 @@ def test_large_state_properties(gpu_ctx):
     a.swap2x2(3, 17, X)
     a.swap2x2(0, 25, X)
     assert a.equal(b)
-    gates = [(0, 0, q, C.G_FIXED) for q in range(11)] + [(1, 20, 4, X), (1, 2, 9, HM)]
+    gates = [(0, 0, q, C.G_FIXED) for q in range(11)] + [(1, 20, 4, X), (1, 2, 9, HM)] + [(0, 0, q, HM) for q in (25, 13, 19, 22)] + [(1, 3, 24, X)]
     a.fused(gates)
     for kind, c, t, m in gates:
         if kind == 0:

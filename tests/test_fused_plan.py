@@ -1,0 +1,59 @@
+"""CPU: how iqsb_fused cuts a batch of gates into shared-memory tile runs (iqsb_plan_fused, pure host code)."""
+import numpy as np
+
+from pkg import capi
+
+H = np.array([1, 0, 1, 0, 1, 0, -1, 0.0]) / np.sqrt(2)
+X = np.array([0, 0, 1, 0, 1, 0, 0, 0.0])
+
+
+def check_cover(gates, runs, M):
+    assert runs[0][0] == 0 and runs[-1][1] == len(gates)
+    for (first, last, tile), nxt in zip(runs, runs[1:] + [None]):
+        assert first < last and len(tile) == min(11, M) and tile == sorted(set(tile))
+        assert tile[: min(4, M)] == list(range(min(4, M)))  # low positions always inside: 256-byte runs
+        for k in range(first, last):
+            assert gates[k][2] in tile  # every target of the run is in its tile
+        if nxt is not None:
+            assert nxt[0] == last
+
+
+def test_layer_of_32_one_qubit_gates_needs_five_sweeps():
+    gates = [(0, 0, q, H) for q in range(32)]
+    runs = capi.plan_fused(gates, 32)
+    check_cover(gates, runs, 32)
+    assert len(runs) == 4  # qubits 0-10, 11-17, 18-24, 25-31
+    assert runs[0][2] == list(range(11))
+
+
+def test_layered_circuit_runs():
+    rng = np.random.default_rng(1)
+    gates = []
+    for layer in range(3):
+        gates += [(0, 0, q, H) for q in range(32)]
+        gates += [(1, q, q + 1, X) for q in range(layer % 2, 31, 2)]
+    runs = capi.plan_fused(gates, 32)
+    check_cover(gates, runs, 32)
+    assert len(runs) <= 24  # 144 gates in at most 24 sweeps
+
+
+def test_random_batches_are_covered_in_order():
+    rng = np.random.default_rng(7)
+    for M in (1, 2, 3, 7, 12, 20, 33):
+        gates = []
+        for i in range(200):
+            t = int(rng.integers(0, M))
+            if M > 1 and i % 2:
+                c = int(rng.integers(0, M))
+                while c == t:
+                    c = int(rng.integers(0, M))
+                gates.append((1, c, t, X))
+            else:
+                gates.append((0, 0, t, H))
+        check_cover(gates, capi.plan_fused(gates, M), M)
+
+
+def test_controls_prefer_tile_slots():
+    gates = [(1, 30, 5, X), (1, 29, 6, X)]
+    (first, last, tile), = capi.plan_fused(gates, 32)
+    assert 30 in tile and 29 in tile  # spare slots are given to the controls of the run

@@ -43,7 +43,7 @@ def classify(prog, n, M):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["qft", "heisenberg", "reorder", "sweep"])
+    ap.add_argument("what", choices=["qft", "heisenberg", "reorder", "sweep", "layered"])
     ap.add_argument("--n", type=int, default=20)
     ap.add_argument("--ranks", type=int, default=1)
     ap.add_argument("--fusion", type=int, default=0)
@@ -54,9 +54,17 @@ def main():
     launcher = [sys.executable, IQSRUN, "-n", str(a.ranks), "--timeout", "1200"] if a.ranks > 1 else None
     runs = []
     if a.what == "qft":
-        runs.append(("qft", C.qft(n), 2, 0))
+        p = C.qft(n)
+        if a.fusion:
+            p = C.Program(n).mode(C.FUSION_ON, a.fusion).extend(p).mode(C.FUSION_OFF)
+        runs.append((f"qft{' fused' if a.fusion else ''}", p, 2, 0))
     elif a.what == "sweep":
         runs.append(("basic_code_for_scaling sweep", C.scaling_sweep(n), 1, 0))
+    elif a.what == "layered":
+        p = C.layered_random(n, 5)
+        if a.fusion:
+            p = C.Program(n).mode(C.FUSION_ON, a.fusion).extend(p).mode(C.FUSION_OFF)
+        runs.append((f"layered random circuit, 5 layers{' fused' if a.fusion else ''}", p, 2, 0))
     elif a.what == "heisenberg":
         p = C.heisenberg_step(n)
         if a.fusion:

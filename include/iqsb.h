@@ -147,7 +147,7 @@ int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates);
 /* tile exponent (11, or log2(local_amps) for tiny shards) */
 int iqsb_fused_max_log2tile(const iqsb_state *st);
 /* Pure host function: the runs iqsb_fused would execute.  run_end[r] = one past the last gate of
- * run r; tiles[12 r] = number of tile positions, tiles[12 r + 1 ..] = the positions (ascending). */
+ * run r; tiles[16 r] = number of tile positions, tiles[16 r + 1 ..] = the positions (ascending); tiles holds 16 bytes per run. */
 int iqsb_plan_fused(const iqsb_fgate *gates, int ngates, unsigned log2_local, int *run_end, uint8_t *tiles, int max_runs, int *nruns);
 
 /* ---- reductions (warp-shuffle + fixed-order second stage; deterministic run to run) -- */

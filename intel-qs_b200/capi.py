@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libiqs_b200.so")
+# IQS_B200_LIB: an alternative build of the same library (kernel tuning variants, tools/fused_variants.sh)
+LIB_PATH = os.environ.get("IQS_B200_LIB") or os.path.join(HERE, "lib", "libiqs_b200.so")
 
 F64, F32 = 0, 1
 MEM_DEVICE, MEM_MANAGED = 0, 1
@@ -56,13 +57,13 @@ def plan_fused(gates, log2_local):
     arr = _fgates(gates)
     n = len(gates)
     run_end = (c_int * max(n, 1))()
-    tiles = np.zeros(12 * max(n, 1), dtype=np.uint8)
+    tiles = np.zeros(16 * max(n, 1), dtype=np.uint8)
     nruns = c_int()
     _chk(load().iqsb_plan_fused(arr, n, log2_local, run_end, tiles.ctypes.data_as(c_vp), max(n, 1), ctypes.byref(nruns)))
     out, first = [], 0
     for r in range(nruns.value):
-        ns = int(tiles[12 * r])
-        out.append((first, int(run_end[r]), tiles[12 * r + 1 : 12 * r + 1 + ns].astype(int).tolist()))
+        ns = int(tiles[16 * r])
+        out.append((first, int(run_end[r]), tiles[16 * r + 1 : 16 * r + 1 + ns].astype(int).tolist()))
         first = int(run_end[r])
     return out
 

@@ -27,10 +27,31 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+// Tuning knobs (compile-time; the defaults are the measured best, profiles/r01_fused_variants.md)
+#ifndef IQSB_FUSED_THREADS
+#define IQSB_FUSED_THREADS 256
+#endif
+#ifndef IQSB_FUSED_MINBLOCKS
+#define IQSB_FUSED_MINBLOCKS 3
+#endif
+#ifndef IQSB_FUSED_TILE
+#define IQSB_FUSED_TILE 12
+#endif
+#ifndef IQSB_FUSED_LOW
+#define IQSB_FUSED_LOW 4
+#endif
+#ifndef IQSB_FUSED_LOADS
+#define IQSB_FUSED_LOADS 4
+#endif
+#ifndef IQSB_FUSED_PAIR_UNROLL
+#define IQSB_FUSED_PAIR_UNROLL 2
+#endif
+constexpr int kThreads = IQSB_FUSED_THREADS;
 constexpr int kMaxFusedGates = 4096;
-constexpr int kTile = 11;  // tile exponent
-constexpr int kLow = 4;    // lowest positions always in the tile
+constexpr int kTile = IQSB_FUSED_TILE;  // tile exponent (<= 12)
+constexpr int kLow = IQSB_FUSED_LOW;    // lowest positions always in the tile
+static_assert(kTile >= 9 && kTile <= 11 + 1 && kLow >= 1 && kLow <= 4, "tile geometry");
+constexpr int kPairUnroll = IQSB_FUSED_PAIR_UNROLL;
 
 template <typename T>
 struct alignas(16) FGate {
@@ -49,100 +70,121 @@ struct TileDesc {
 // 16-byte slots; swizzle so that pairs (i, i + 2^s) are conflict free for every s
 __device__ __forceinline__ unsigned phys(unsigned i) { return i ^ (((i >> 3) & 1u) * 7u); }
 
-template <typename T>
-__device__ __forceinline__ FGate<T> load_gate(const FGate<T> *p) {
-  FGate<T> g;
-  const int4 *src = reinterpret_cast<const int4 *>(p);
-  int4 *dst = reinterpret_cast<int4 *>(&g);
+// global <-> tile, U 32-byte accesses in flight per thread; nchunks is a multiple of kThreads * U
+template <typename T, int U>
+__device__ __forceinline__ void tile_load(Cx<T> *tile, const Chunk<T> *g, const uint64_t *g_lo, const uint64_t *g_hi, unsigned nchunks) {
+#pragma unroll 1
+  for (unsigned c0 = threadIdx.x; c0 < nchunks; c0 += kThreads * U) {
+    Chunk<T> v[U];
 #pragma unroll
-  for (int i = 0; i < (int)(sizeof(FGate<T>) / 16); ++i) dst[i] = __ldg(src + i);
-  return g;
+    for (int u = 0; u < U; ++u) {
+      unsigned c = c0 + u * kThreads;
+      v[u] = ld_chunk(g + (g_lo[c & 255] | g_hi[c >> 8]));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      unsigned c = c0 + u * kThreads;
+      tile[phys(2 * c)] = v[u].a;
+      tile[phys(2 * c + 1)] = v[u].b;
+    }
+  }
+}
+template <typename T, int U>
+__device__ __forceinline__ void tile_store(const Cx<T> *tile, Chunk<T> *g, const uint64_t *g_lo, const uint64_t *g_hi, unsigned nchunks) {
+#pragma unroll 1
+  for (unsigned c0 = threadIdx.x; c0 < nchunks; c0 += kThreads * U) {
+    Chunk<T> v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      unsigned c = c0 + u * kThreads;
+      v[u].a = tile[phys(2 * c)];
+      v[u].b = tile[phys(2 * c + 1)];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      unsigned c = c0 + u * kThreads;
+      st_chunk(g + (g_lo[c & 255] | g_hi[c >> 8]), v[u]);
+    }
+  }
 }
 
+constexpr int kGateBatch = 16;  // gate descriptors staged in shared memory at a time
+
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
     k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, const FGate<T> *__restrict__ gates, int ngates) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cx<T> *tile = reinterpret_cast<Cx<T> *>(smem_raw);
   // chunk offset of tile-local chunk index c = lo | hi << 8 (c = tile-local amplitude index / 2)
-  __shared__ uint64_t g_lo[256], g_hi[4];
+  __shared__ uint64_t g_lo[256], g_hi[8];
+  __shared__ __align__(16) FGate<T> s_gate[kGateBatch];
+  __shared__ int s_pos[16];
   const int nS = td.nS;  // pos[0] == 0 always
-  for (unsigned t = threadIdx.x; t < 256 + 4; t += kThreads) {
+  if (threadIdx.x < kTile) s_pos[threadIdx.x] = td.pos[threadIdx.x];
+  __syncthreads();
+  for (unsigned t = threadIdx.x; t < 256 + 8; t += kThreads) {
     unsigned v = t < 256 ? t : (t - 256) << 8;
     uint64_t go = 0;
+#pragma unroll 1
     for (int k = 1; k < nS; ++k)
-      if ((v >> (k - 1)) & 1u) go |= 1ull << (td.pos[k] - 1);
+      if ((v >> (k - 1)) & 1u) go |= 1ull << (s_pos[k] - 1);
     if (t < 256) g_lo[t] = go;
     else g_hi[t - 256] = go;
   }
   __syncthreads();
   const unsigned nchunks = 1u << (nS - 1);
-  constexpr int U = 4;  // 32-byte loads in flight per thread
+  constexpr int U = IQSB_FUSED_LOADS;  // 32-byte loads in flight per thread
   for (uint64_t o = blockIdx.x; o < nouter; o += gridDim.x) {
     uint64_t base = o;  // amplitude index with zeros at the tile positions
-    for (int k = 0; k < nS; ++k) base = insert_zero(base, td.pos[k]);
+#pragma unroll 1
+    for (int k = 0; k < nS; ++k) base = insert_zero(base, (unsigned)s_pos[k]);
     Chunk<T> *g = state + (base >> 1);
-    for (unsigned c0 = threadIdx.x; c0 < nchunks; c0 += kThreads * U) {
-      Chunk<T> v[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        unsigned c = c0 + u * kThreads;
-        if (c < nchunks) v[u] = ld_chunk(g + (g_lo[c & 255] | g_hi[c >> 8]));
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        unsigned c = c0 + u * kThreads;
-        if (c < nchunks) {
-          tile[phys(2 * c)] = v[u].a;
-          tile[phys(2 * c + 1)] = v[u].b;
-        }
-      }
-    }
-    __syncthreads();
-    for (int gi = 0; gi < ngates; ++gi) {
-      const FGate<T> G = load_gate(gates + gi);
-      const unsigned ts = (unsigned)G.tslot;
-      if (G.ckind == 2 && !((base >> G.c) & 1ull)) continue;  // uniform over the CTA
-      if (G.ckind != 1) {
-        const unsigned npairs = 1u << (nS - 1);
-        for (unsigned j = threadIdx.x; j < npairs; j += kThreads) {
-          unsigned i0 = (unsigned)insert_zero(j, ts), i1 = i0 | (1u << ts);
-          Cx<T> a = tile[phys(i0)], b = tile[phys(i1)];
-          apply2x2(G.m, a, b);
-          tile[phys(i0)] = a;
-          tile[phys(i1)] = b;
-        }
-      } else {
-        const unsigned cs = (unsigned)G.c;
-        const unsigned lo = cs < ts ? cs : ts, hi = cs < ts ? ts : cs;
-        const unsigned npairs = 1u << (nS - 2);
-        for (unsigned j = threadIdx.x; j < npairs; j += kThreads) {
-          unsigned x = (unsigned)insert_zero(insert_zero(j, lo), hi);
-          unsigned i0 = x | (1u << cs), i1 = i0 | (1u << ts);
-          Cx<T> a = tile[phys(i0)], b = tile[phys(i1)];
-          apply2x2(G.m, a, b);
-          tile[phys(i0)] = a;
-          tile[phys(i1)] = b;
-        }
-      }
+    if (nchunks % (kThreads * U) == 0) tile_load<T, U>(tile, g, g_lo, g_hi, nchunks);
+    else tile_load<T, 1>(tile, g, g_lo, g_hi, nchunks);
+    for (int g0 = 0; g0 < ngates; g0 += kGateBatch) {
+      // stage the next descriptors (the barrier also orders the tile accesses of the previous gate)
+      const int nb = ngates - g0 < kGateBatch ? ngates - g0 : kGateBatch;
+      constexpr int kWords = (int)(sizeof(FGate<T>) / 16);
+      if (g0) __syncthreads();  // a skipped gate has no barrier of its own: nobody still reads s_gate
+      if ((int)threadIdx.x < nb * kWords)
+        reinterpret_cast<int4 *>(s_gate)[threadIdx.x] = __ldg(reinterpret_cast<const int4 *>(gates + g0) + threadIdx.x);
       __syncthreads();
-    }
-    for (unsigned c0 = threadIdx.x; c0 < nchunks; c0 += kThreads * U) {
-      Chunk<T> v[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        unsigned c = c0 + u * kThreads;
-        if (c < nchunks) {
-          v[u].a = tile[phys(2 * c)];
-          v[u].b = tile[phys(2 * c + 1)];
+      for (int gi = 0; gi < nb; ++gi) {
+        const unsigned ts = (unsigned)s_gate[gi].tslot;
+        const int ckind = s_gate[gi].ckind;
+        const unsigned cs = (unsigned)s_gate[gi].c;
+        if (ckind == 2 && !((base >> cs) & 1ull)) continue;  // uniform over the CTA
+        const Mat2<T> m = s_gate[gi].m;
+        if (ckind != 1) {
+          const unsigned npairs = 1u << (nS - 1);
+#pragma unroll kPairUnroll
+          for (unsigned j = threadIdx.x; j < npairs; j += kThreads) {
+            const unsigned x = (unsigned)insert_zero(j, ts);
+            const unsigned i0 = phys(x), i1 = phys(x | (1u << ts));
+            Cx<T> a = tile[i0], b = tile[i1];
+            apply2x2(m, a, b);
+            tile[i0] = a;
+            tile[i1] = b;
+          }
+        } else {
+          const unsigned lo = cs < ts ? cs : ts, hi = cs < ts ? ts : cs;
+          const unsigned npairs = 1u << (nS - 2);
+#pragma unroll kPairUnroll
+          for (unsigned j = threadIdx.x; j < npairs; j += kThreads) {
+            const unsigned x = (unsigned)insert_zero(insert_zero(j, lo), hi) | (1u << cs);
+            const unsigned i0 = phys(x), i1 = phys(x | (1u << ts));
+            Cx<T> a = tile[i0], b = tile[i1];
+            apply2x2(m, a, b);
+            tile[i0] = a;
+            tile[i1] = b;
+          }
         }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        unsigned c = c0 + u * kThreads;
-        if (c < nchunks) st_chunk(g + (g_lo[c & 255] | g_hi[c >> 8]), v[u]);
+        __syncthreads();
       }
     }
+    __syncthreads();  // covers ngates == 0 and a skipped last gate
+    if (nchunks % (kThreads * U) == 0) tile_store<T, U>(tile, g, g_lo, g_hi, nchunks);
+    else tile_store<T, 1>(tile, g, g_lo, g_hi, nchunks);
     __syncthreads();
   }
 }
@@ -201,7 +243,7 @@ extern "C" int iqsb_fused_max_log2tile(const iqsb_state *st) {
 }
 
 // Pure host function: how iqsb_fused cuts a batch into runs.  run_end[r] = index one past the last
-// gate of run r; tiles[r*12] = number of tile positions, tiles[r*12 + 1 ..] = the positions.
+// gate of run r; tiles[r*16] = number of tile positions, tiles[r*16 + 1 ..] = the positions.
 extern "C" int iqsb_plan_fused(const iqsb_fgate *gates, int ngates, unsigned log2_local, int *run_end, uint8_t *tiles, int max_runs, int *nruns) {
   IQSB_REQUIRE((gates || ngates == 0) && run_end && tiles && nruns && max_runs > 0, "iqsb_plan_fused: null argument");
   const unsigned K = log2_local < (unsigned)kTile ? log2_local : (unsigned)kTile;
@@ -227,12 +269,12 @@ extern "C" int iqsb_plan_fused(const iqsb_fgate *gates, int ngates, unsigned log
       if (gates[k].kind == 1 && (unsigned)gates[k].control < log2_local && !in[gates[k].control]) { in[gates[k].control] = true; ++cnt; }
     for (unsigned b = 0; b < log2_local && cnt < K; ++b)
       if (!in[b]) { in[b] = true; ++cnt; }
-    uint8_t *td = tiles + r * 12;
+    uint8_t *td = tiles + r * 16;
     td[0] = (uint8_t)cnt;
     int n = 0;
     for (unsigned b = 0; b < log2_local; ++b)
       if (in[b]) td[1 + n++] = (uint8_t)b;
-    for (; n < kTile; ++n) td[1 + n] = 0;
+    for (; n < 15; ++n) td[1 + n] = 0;
     run_end[r++] = last;
     first = last;
   }
@@ -260,14 +302,14 @@ extern "C" int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates) {
     return IQSB_OK;
   }
   std::vector<int> run_end((size_t)ngates);
-  std::vector<uint8_t> tiles((size_t)ngates * 12);
+  std::vector<uint8_t> tiles((size_t)ngates * 16);
   int nruns = 0;
   IQSB_TRY(iqsb_plan_fused(gates, ngates, st->log2_local, run_end.data(), tiles.data(), ngates, &nruns));
   int first = 0;
   for (int r = 0; r < nruns; ++r) {
     TileDesc td;
-    td.nS = tiles[r * 12];
-    for (int k = 0; k < kTile; ++k) td.pos[k] = tiles[r * 12 + 1 + k];
+    td.nS = tiles[r * 16];
+    for (int k = 0; k < kTile; ++k) td.pos[k] = tiles[r * 16 + 1 + k];
     int rc = st->dtype == IQSB_F64 ? launch_run<double>(st, gates, first, run_end[r], td) : launch_run<float>(st, gates, first, run_end[r], td);
     if (rc != IQSB_OK) return rc;
     first = run_end[r];

@@ -5,12 +5,13 @@ from pkg import capi
 
 H = np.array([1, 0, 1, 0, 1, 0, -1, 0.0]) / np.sqrt(2)
 X = np.array([0, 0, 1, 0, 1, 0, 0, 0.0])
+K = len(capi.plan_fused([(0, 0, 0, H)], 40)[0][2])  # tile exponent the library was built with
 
 
 def check_cover(gates, runs, M):
     assert runs[0][0] == 0 and runs[-1][1] == len(gates)
     for (first, last, tile), nxt in zip(runs, runs[1:] + [None]):
-        assert first < last and len(tile) == min(11, M) and tile == sorted(set(tile))
+        assert first < last and len(tile) == min(K, M) and tile == sorted(set(tile))
         assert tile[: min(4, M)] == list(range(min(4, M)))  # low positions always inside: 256-byte runs
         for k in range(first, last):
             assert gates[k][2] in tile  # every target of the run is in its tile
@@ -18,12 +19,12 @@ def check_cover(gates, runs, M):
             assert nxt[0] == last
 
 
-def test_layer_of_32_one_qubit_gates_needs_five_sweeps():
+def test_layer_of_32_one_qubit_gates_needs_four_sweeps():
     gates = [(0, 0, q, H) for q in range(32)]
     runs = capi.plan_fused(gates, 32)
     check_cover(gates, runs, 32)
-    assert len(runs) == 4  # qubits 0-10, 11-17, 18-24, 25-31
-    assert runs[0][2] == list(range(11))
+    assert len(runs) == 1 + -(-(32 - K) // (K - 4))  # K = 11: qubits 0-10, 11-17, 18-24, 25-31
+    assert runs[0][2] == list(range(K))
 
 
 def test_layered_circuit_runs():

@@ -1,0 +1,25 @@
+#!/bin/bash
+# Build tuning variants of the fused kernel (compile-time knobs of csrc/kernels_fused.cu) as
+# build/variants/<name>/libiqs_b200.so; tools/kbench.py picks one with IQS_B200_LIB=<path>.
+set -e
+cd "$(dirname "$0")/.."
+python -c "import __graft_entry__ as g; g.build()" >/dev/null
+variants=(
+  "mb2u1:-DIQSB_FUSED_MINBLOCKS=2 -DIQSB_FUSED_PAIR_UNROLL=1"
+  "mb2u2:-DIQSB_FUSED_MINBLOCKS=2 -DIQSB_FUSED_PAIR_UNROLL=2"
+  "mb3u1:-DIQSB_FUSED_MINBLOCKS=3 -DIQSB_FUSED_PAIR_UNROLL=1"
+  "mb3u2:-DIQSB_FUSED_MINBLOCKS=3 -DIQSB_FUSED_PAIR_UNROLL=2"
+  "mb4u1:-DIQSB_FUSED_MINBLOCKS=4 -DIQSB_FUSED_PAIR_UNROLL=1"
+  "t12mb2u1:-DIQSB_FUSED_TILE=12 -DIQSB_FUSED_MINBLOCKS=2 -DIQSB_FUSED_PAIR_UNROLL=1"
+  "t12mb3u1:-DIQSB_FUSED_TILE=12 -DIQSB_FUSED_MINBLOCKS=3 -DIQSB_FUSED_PAIR_UNROLL=1"
+  "t12th512:-DIQSB_FUSED_TILE=12 -DIQSB_FUSED_THREADS=512 -DIQSB_FUSED_MINBLOCKS=1 -DIQSB_FUSED_PAIR_UNROLL=1"
+)
+for v in "${variants[@]}"; do
+  name=${v%%:*}; flags=${v#*:}
+  d=build/variants/$name; mkdir -p $d
+  echo "== $name $flags"
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -ccbin /usr/bin/g++ -Wno-deprecated-gpu-targets \
+    -Xptxas -v $flags -c intel-qs_b200/csrc/kernels_fused.cu -o $d/kernels_fused.o 2>&1 | grep -A2 "k_fusedId" | grep -E "Used|spill" || true
+  objs=$(ls build/*.o | grep -v "host_\|kernels_fused.o")
+  nvcc -shared -ccbin /usr/bin/g++ -Wno-deprecated-gpu-targets -o $d/libiqs_b200.so $objs $d/kernels_fused.o -ldl
+done

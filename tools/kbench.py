@@ -91,6 +91,15 @@ def main():
         for ng in (1, 4, 8, 16, 32):
             gates = [(0, 0, i % 11, C.G_FIXED) for i in range(ng)]
             timeit(f"fused{ng}", "-", lambda gates=gates: st.fused(gates), 32.0 * L)
+        # one run whose tile is built from positions scattered over the whole index (4 low + 7 high)
+        hi = [n - 1 - 3 * i for i in range(7)]
+        for ng in (1, 7, 28):
+            gates = [(0, 0, hi[i % 7], C.G_FIXED) for i in range(ng)]
+            timeit(f"fused_hi{ng}", "-", lambda gates=gates: st.fused(gates), 32.0 * L)
+        # a layer of one-qubit gates on every qubit followed by a CX chain (several runs)
+        gates = [(0, 0, q, C.G_FIXED) for q in range(n)] + [(1, q, q + 1, X) for q in range(0, n - 1, 2)]
+        runs = len(capi.plan_fused(gates, n))
+        timeit(f"fused_layer{len(gates)}g{runs}r", "-", lambda gates=gates: st.fused(gates), 32.0 * L * runs)
     if "gate2" in ops:
         rng = np.random.default_rng(0)
         q, _ = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))

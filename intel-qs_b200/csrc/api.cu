@@ -84,6 +84,8 @@ extern "C" int iqsb_finalize(iqsb_ctx *ctx) {
   cudaFree(ctx->d_result);
   cudaFree(ctx->d_flags);
   cudaFreeHost(ctx->h_result);
+  cudaFreeHost(ctx->stage_h);
+  cudaFree(ctx->stage_d);
   if (ctx->slots) {
     for (int i = 0; i < kMaxEventSlots; ++i)
       if (ctx->slots[i]) cudaEventDestroy(ctx->slots[i]);

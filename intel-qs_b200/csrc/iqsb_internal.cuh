@@ -61,7 +61,12 @@ struct iqsb_ctx {
   int *d_flags = nullptr;        // [4]
   void *comm = nullptr;          // ncclComm_t
   iqsb_peer_table *peers = nullptr;
+  // staging ring for small argument lists (fused gate descriptors): pinned host bytes mirrored at
+  // the same offsets in device memory, consumed in stream order, so no host synchronisation per use
+  unsigned char *stage_h = nullptr, *stage_d = nullptr;
+  size_t stage_off = 0;
 };
+constexpr size_t kStageBytes = 1u << 20;
 
 struct iqsb_state {
   iqsb_ctx *ctx = nullptr;

@@ -210,15 +210,23 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, int first, int last, const 
       else { o.ckind = 2; o.c = c; }
     }
   }
-  FGate<T> *d = nullptr;
-  size_t bytes = sizeof(FGate<T>) * gates.size();
-  cudaError_t e = cudaMallocAsync((void **)&d, bytes, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d, gates.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `gates` is pageable
-  if (e != cudaSuccess) {
-    iqsb_set_error("iqsb_fused: staging the gate list failed: %s", cudaGetErrorString(e));
-    return IQSB_ERR_CUDA;
+  // descriptors travel through the context's staging ring: written into pinned memory, copied in
+  // stream order; the host only waits when the ring wraps around
+  const size_t bytes = sizeof(FGate<T>) * gates.size();
+  if (!ctx->stage_h) {
+    IQSB_CUDA(cudaMallocHost((void **)&ctx->stage_h, kStageBytes));
+    IQSB_CUDA(cudaMalloc((void **)&ctx->stage_d, kStageBytes));
+    ctx->stage_off = 0;
   }
+  IQSB_REQUIRE(bytes <= kStageBytes, "iqsb_fused: gate list too long for the staging ring");
+  if (ctx->stage_off + bytes > kStageBytes) {
+    IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stage_off = 0;
+  }
+  memcpy(ctx->stage_h + ctx->stage_off, gates.data(), bytes);
+  FGate<T> *d = reinterpret_cast<FGate<T> *>(ctx->stage_d + ctx->stage_off);
+  IQSB_CUDA(cudaMemcpyAsync(d, ctx->stage_h + ctx->stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->stage_off += (bytes + 255) & ~(size_t)255;
   size_t smem = (size_t)sizeof(Cx<T>) << td.nS;
   IQSB_CUDA(cudaFuncSetAttribute(k_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
@@ -228,9 +236,7 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, int first, int last, const 
   uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
   unsigned grid = (unsigned)(nouter < cap ? nouter : cap);
   k_fused<T><<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, (int)gates.size());
-  int rc = iqsb_check_launch(ctx, "k_fused");
-  cudaFreeAsync(d, ctx->stream);
-  return rc;
+  return iqsb_check_launch(ctx, "k_fused");
 }
 
 }  // namespace

@@ -309,6 +309,7 @@ using BaseType = typename QubitRegister<Type>::BaseType;
 
 }  // namespace iqs
 
-// Derived class that counts gates and depth (as the reference does at the end of qureg.hpp).
-// NoisyQureg (automatic noise insertion) is outside the B200 scope and is not provided.
+// Derived classes, included at the end of qureg.hpp as the reference does (qureg.hpp:432-433):
+// gate/depth counting and automatic insertion of noise gates.
 #include "QubitRegisterMetric.hpp"
+#include "NoisyQureg.hpp"

@@ -553,8 +553,10 @@ void QubitRegister<Type>::ApplyDiagGeneral(unsigned qubit_1, unsigned qubit_2, T
 
 template <class Type>
 void QubitRegister<Type>::Apply2QubitGate(unsigned const qubit_high, unsigned const qubit_low, TM4x4<Type> const &m) {
-  // single-rank only, like the reference (2q.cpp:23); the basis index is 2*bit(high) + bit(low)
-  assert(iqs::mpi::Environment::GetStateSize() == 1);
+  // the basis index is 2*bit(high) + bit(low).  The reference is single-rank only (2q.cpp:23:
+  // assert on the state size).  Here a global position is first exchanged with a free local one
+  // (exact data movement over NVLink: the SWAP path with m = X), the 4x4 is applied locally and the
+  // exchange is undone -- so the gathered state equals the single-rank result bit for bit.
   assert(qubit_low < num_qubits && qubit_high < num_qubits && qubit_low != qubit_high);
   if (fusion == true) ApplyFusedGates();
   unsigned position_high = (*qubit_permutation)[qubit_high];
@@ -566,7 +568,29 @@ void QubitRegister<Type>::Apply2QubitGate(unsigned const qubit_high, unsigned co
       mm[2 * (4 * i + j) + 1] = m[i][j].imag();
     }
   BeforeDeviceOp();
-  Check(iqsb_gate2(dev_, position_high, position_low, mm), "Apply2QubitGate");
+  const unsigned M = LocalQubits();
+  const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+  unsigned pos[2] = {position_high, position_low};
+  unsigned moved_from[2], moved_to[2];
+  int nmoved = 0;
+  if (position_high >= M || position_low >= M) {
+    if (M < 2) throw std::invalid_argument("Apply2QubitGate on global qubits needs at least two local qubits");
+    unsigned candidate = M;  // highest free local position first
+    for (int k = 0; k < 2; ++k) {
+      if (pos[k] < M) continue;
+      do {
+        --candidate;
+      } while (candidate == pos[0] || candidate == pos[1]);
+      Check(iqsb_swap2x2_global(dev_, M, candidate, pos[k], X), "Apply2QubitGate: bringing a global qubit to a local position");
+      moved_from[nmoved] = pos[k];
+      moved_to[nmoved] = candidate;
+      ++nmoved;
+      pos[k] = candidate;
+    }
+  }
+  Check(iqsb_gate2(dev_, pos[0], pos[1], mm), "Apply2QubitGate");
+  for (int k = nmoved - 1; k >= 0; --k)
+    Check(iqsb_swap2x2_global(dev_, M, moved_to[k], moved_from[k], X), "Apply2QubitGate: returning a qubit to its global position");
   if (gate_counter != nullptr) gate_counter->TwoQubitIncrement(qubit_high, qubit_low);
 }
 
@@ -584,11 +608,26 @@ void QubitRegister<Type>::ApplyToffoli(unsigned const control_1, unsigned const 
   V_dag(0, 1) = {1.0 / 2.0, -1.0 / 2.0};
   V_dag(1, 0) = {1.0 / 2.0, -1.0 / 2.0};
   V_dag(1, 1) = {1.0 / 2.0, 1.0 / 2.0};
+  // With all three qubits local the five gates go through the fusion queue as one batch: the same
+  // arithmetic in the same order, but ONE sweep of the state (a shared-memory tile holding the three
+  // positions) instead of five half-sweeps.
+  unsigned M = LocalQubits();
+  bool batch = !fusion && M >= 4 && (*qubit_permutation)[control_1] < M && (*qubit_permutation)[control_2] < M && (*qubit_permutation)[target] < M;
+  unsigned saved_log2llc = log2llc;
+  if (batch) {
+    log2llc = M;
+    fusion = true;
+  }
   ApplyControlled1QubitGate(control_1, target, V);
   ApplyCPauliX(control_2, control_1);
   ApplyControlled1QubitGate(control_1, target, V_dag);
   ApplyCPauliX(control_2, control_1);
   ApplyControlled1QubitGate(control_2, target, V);
+  if (batch) {
+    ApplyFusedGates();
+    fusion = false;
+    log2llc = saved_log2llc;
+  }
 }
 
 // =============================================================================================

@@ -137,13 +137,65 @@ void QubitRegister<Type>::ApplyNoiseGate(unsigned qubit, BaseType duration) {
   QubitRegister<Type>::Apply1QubitGate(qubit, U_noise);
 }
 
-template <class Type>
-void QubitRegister<Type>::ApplyChannel(const unsigned, CM4x4<Type> &) {
-  throw std::runtime_error("QubitRegister::ApplyChannel: quantum channels (chi-matrix eigen-decomposition) are outside the scope of the B200 engine");
+// Quantum channels through the chi matrix (reference src/qureg_apply_channel.cpp:18-112): draw one
+// eigen-operator of chi with probability |E_k| / sum |E_k| and apply it as a gate.  The operator is
+// sum_i E_k,i sigma_i in the Pauli basis {id, X, Y, Z}; it is in general not unitary, averages over
+// many trajectories reproduce the channel.
+namespace {
+template <class Type, class Chi>
+unsigned DrawEigenOperator(iqs::RandomNumberGenerator<typename QubitRegister<Type>::BaseType> *rng, Chi &chi, unsigned dim) {
+  typename QubitRegister<Type>::BaseType r;
+  rng->UniformRandomNumbers(&r, 1, 0, 1, "state");
+  unsigned k = 0;
+  while (r > chi.GetEigenCumulativeProbability(k)) {
+    ++k;
+    if (k >= dim) {
+      assert(0 && "Error: p_cum should be normalized to 1.");
+      throw std::runtime_error("ApplyChannel: the eigen-probabilities of the chi matrix do not sum to 1 (was SolveEigenSystem called?)");
+    }
+  }
+  return k;
 }
+}  // namespace
+
 template <class Type>
-void QubitRegister<Type>::ApplyChannel(const unsigned, const unsigned, CM16x16<Type> &) {
-  throw std::runtime_error("QubitRegister::ApplyChannel: quantum channels (chi-matrix eigen-decomposition) are outside the scope of the B200 engine");
+void QubitRegister<Type>::ApplyChannel(const unsigned qubit, CM4x4<Type> &chi) {
+  assert(rng_ptr_ != nullptr);
+  const unsigned k = DrawEigenOperator<Type>(rng_ptr_, chi, 4);
+  const std::vector<Type> e = chi.GetEigenVector(k);
+  const Type I(0., 1.);
+  TM2x2<Type> op;  // e0 id + e1 X + e2 Y + e3 Z
+  op(0, 0) = e[0] + e[3];
+  op(0, 1) = e[1] - I * e[2];
+  op(1, 0) = e[1] + I * e[2];
+  op(1, 1) = e[0] - e[3];
+  if (std::real(chi.GetEigenValue(k)) < 0) overall_sign_of_channels *= -1;  // negative weight of the trajectory
+  Apply1QubitGate(qubit, op);
+}
+
+template <class Type>
+void QubitRegister<Type>::ApplyChannel(const unsigned qubit1, const unsigned qubit2, CM16x16<Type> &chi) {
+  assert(rng_ptr_ != nullptr);
+  const unsigned k = DrawEigenOperator<Type>(rng_ptr_, chi, 16);
+  const std::vector<Type> e = chi.GetEigenVector(k);
+  // op = sum_ab e[4a+b] sigma_a (x) sigma_b, rows/columns indexed 2*bit(qubit1) + bit(qubit2).  Like
+  // the reference (apply_channel.cpp:87-104) the upper triangle and the diagonal are that expansion
+  // and the lower triangle is its conjugate: the operator is taken as Hermitian.
+  const Type I(0., 1.), one(1., 0.), zero(0., 0.);
+  const Type pauli[4][2][2] = {{{one, zero}, {zero, one}}, {{zero, one}, {one, zero}}, {{zero, -I}, {I, zero}}, {{one, zero}, {zero, -one}}};
+  TM4x4<Type> op;
+  for (unsigned r = 0; r < 4; ++r)
+    for (unsigned c = r; c < 4; ++c) {
+      Type sum = zero;
+      for (unsigned a = 0; a < 4; ++a)
+        for (unsigned b = 0; b < 4; ++b) {
+          const Type w = pauli[a][r >> 1][c >> 1] * pauli[b][r & 1][c & 1];
+          if (w != zero) sum += w * e[4 * a + b];
+        }
+      op(r, c) = sum;
+      if (c != r) op(c, r) = std::conj(sum);
+    }
+  Apply2QubitGate(qubit1, qubit2, op);
 }
 
 template class QubitRegister<ComplexSP>;

@@ -18,6 +18,9 @@ COMMANDS = {
     "specv2_bench": ["10", "1"],
     "get_started_with_IQS": [],
     "communication_reduction_via_qubit_reordering": ["22"],
+    "circuit_with_noise_gates": ["8"],
+    "get_started_with_noisy_IQS": [],
+    # (noise_via_chi_matrix needs the reference configured with Eigen: no fixture, see the test)
 }
 
 # the QASM interpreter reads its program from stdin (interface/src/interface_api_qasm.cpp:109-125)
@@ -31,6 +34,9 @@ if __name__ == "__main__":
     r = subprocess.run([os.path.join(BIN, "qaoa_check")], capture_output=True, text=True, env=env, timeout=600)
     open(os.path.join(HERE, "examples", "qaoa_check.txt"), "w").write(f"EXIT {r.returncode}\n" + r.stdout)
     print("qaoa_check exit", r.returncode)
+    r = subprocess.run([os.path.join(BIN, "noise_check")], capture_output=True, text=True, env=env, timeout=600)
+    open(os.path.join(HERE, "examples", "noise_check.txt"), "w").write(f"EXIT {r.returncode}\n" + r.stdout)
+    print("noise_check exit", r.returncode)
     for name, args in COMMANDS.items():
         r = subprocess.run([os.path.join(BIN, name)] + args, capture_output=True, text=True, env=env, timeout=600)
         # (benchgates ends with `return 1` also on success; the exit code is part of the fixture)

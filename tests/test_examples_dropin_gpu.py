@@ -19,7 +19,7 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "dropin", "bin")
 GOLD = os.path.join(HERE, "golden", "examples")
 
 NUM = re.compile(r"[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eE][-+]?\d+)?")
-SKIP = re.compile(r"seconds|Simulation time|OMP number of threads|statistics|IqsMPI|INTELQS_HAS_MPI|Fusion is|Compiler flags|-->|Time |time ", re.I)
+SKIP = re.compile(r"MPI not enabled|seconds|Simulation time|OMP number of threads|statistics|IqsMPI|INTELQS_HAS_MPI|Fusion is|Compiler flags|-->|Time |time ", re.I)
 
 
 def run(name, args, stdin=None):
@@ -48,15 +48,22 @@ def same(a, b, tol):
     return len(xa) == len(xb) and all(abs(p - q) <= tol for p, q in zip(xa, xb))
 
 
-def compare(name, args, tol=1e-7, rc_must_match=True, stdin=None):
+def compare(name, args, tol=1e-7, rc_must_match=True, stdin=None, until=None):
+    """until: a marker line; what the drop-in build prints from there on has no reference counterpart"""
     want_rc, want = golden(name)
     rc, out, err = run(name, args, stdin)
     if rc_must_match:
         assert rc == want_rc, f"{name}: exit {rc}, reference exits {want_rc}\n{err[-1500:]}"
-    got, want = keep(out.splitlines()), keep(want)
+    lines = out.splitlines()
+    if until is not None:
+        cut = [i for i, l in enumerate(lines) if l.startswith(until)]
+        assert cut, f"{name}: marker {until!r} not printed"
+        lines, extra = lines[: cut[0]], lines[cut[0] + 1 :]
+    got, want = keep(lines), keep(want)
     assert len(got) == len(want), f"{name}: {len(got)} lines vs {len(want)} in the reference output\n" + "\n".join(got[-15:])
     for g, w in zip(got, want):
         assert same(g, w, tol), f"{name}:\n  ours: {g}\n  ref : {w}"
+    return extra if until is not None else None
 
 
 def test_grover_4qubit():
@@ -123,3 +130,39 @@ def test_qaoa_features():
     order), QAOA layers, cost expectation values and the three histograms, against the reference's
     own qaoa_features.cpp run on the CPU."""
     compare("qaoa_check", [], tol=2e-12)
+
+
+def test_circuit_with_noise_gates_example():
+    """examples/circuit_with_noise_gates.cpp: 2 x 200 stochastic circuits through iqs::NoisyQureg
+    (include/NoisyQureg.hpp); the seeded std::default_random_engine makes the run reproducible, so
+    the averaged overlaps must print as in the reference build."""
+    compare("circuit_with_noise_gates", ["8"], tol=2e-6)
+
+
+def test_noisy_tutorial():
+    """tutorials/get_started_with_noisy_IQS.cpp: ApplyNoiseGate on the RNG stream "state", 2 x 200
+    trajectories, pool sums (the program ends with `return 1`)."""
+    compare("get_started_with_noisy_IQS", [], tol=2e-6)
+
+
+def test_noise_scenario():
+    """tests/noise_check.cpp: every NoisyQureg method, ApplyNoiseGate, ApplyChannel with the closed-form
+    Hadamard eigensystem -- amplitudes against the reference build; then (B200 build only, the
+    reference needs Eigen) the depolarising channel and a two-qubit channel through the eigen-solver."""
+    extra = compare("noise_check", [], tol=2e-12, until="==== eigen-solver part")
+    assert any(l.startswith("depolarising OK") for l in extra), extra
+    assert any(l.startswith("CZ channel") and l.endswith("OK") for l in extra), extra
+    assert not any("FAILED" in l for l in extra)
+
+
+def test_noise_via_chi_matrix_example():
+    """examples/noise_via_chi_matrix.cpp: the reference build aborts here (SolveEigenSystem asserts
+    without Eigen), so the program's own statement is the check: the channel is an ideal Hadamard,
+    the noisy ensemble must equal the noiseless circuit."""
+    rc, out, err = run("noise_via_chi_matrix", ["8"])
+    assert rc == 1, err[-1500:]  # the program ends with `return 1`
+    ov = re.search(r"Overlap-squared between ideal and noisy states = ([-+0-9.eE]+)", out)
+    p0 = re.search(r"in the noiseless case = ([-+0-9.eE]+)", out)
+    p1 = re.search(r"with noise = ([-+0-9.eE]+)", out)
+    assert ov and abs(float(ov.group(1)) - 1.0) < 1e-6
+    assert p0 and p1 and abs(float(p0.group(1)) - float(p1.group(1))) < 1e-6

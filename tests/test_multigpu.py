@@ -102,3 +102,25 @@ def test_fusion_sharded(oracle, nranks):
     want, _, _ = oracle.run_program(n, psi, prog.ops)
     got = run_ranks(oracle, nranks, prog, state=psi)
     assert np.array_equal(got["state"], want)
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_two_qubit_gate_on_global_qubits(oracle, nranks):
+    """Apply2QubitGate with one or both qubits global (the reference asserts a single rank,
+    qureg_apply2qubitgate.cpp:23): global positions are exchanged with local ones by exact moves,
+    so the gathered state equals the single-rank oracle bit for bit."""
+    need(nranks)
+    n = 10
+    rng = np.random.Generator(np.random.MT19937(17))
+    prog = C.Program(n)
+    pairs = [(n - 1, 0), (0, n - 1), (n - 1, n - 2), (n - 2, n - 1), (3, 5), (n - 1, n - 3), (n - 4, n - 1)]
+    pairs += [tuple(int(x) for x in rng.permutation(n)[:2]) for _ in range(12)]
+    for qh, ql in pairs:
+        a = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+        u, _ = np.linalg.qr(a)
+        prog.gate2(qh, ql, u)
+        prog.named1(C.H, int(rng.integers(0, n)))
+    psi = C.random_state(n, 8)
+    want, _, _ = oracle.run_program(n, psi, prog.ops)
+    got = run_ranks(oracle, nranks, prog, state=psi)
+    assert np.array_equal(got["state"], want)

@@ -4,7 +4,7 @@
 // pybind11/intelqs_py.cpp:56-426: EnvInit/EnvFinalize, QubitRegister with the NumPy buffer
 // protocol, named gates, custom 2x2 gates from a complex128 array, measurement, expectation
 // values, RandomNumberGenerator, MPIEnvironment statics), so notebooks and scripts written for
-// Intel-QS run unchanged.  Channels (CM4x4 / CM16x16) are outside the B200 scope and are not bound.  Additions (marked "B200") expose what the reference's module lacks.
+// Intel-QS run unchanged.  Additions (marked "B200") expose what the reference's module lacks.
 #include <pybind11/complex.h>
 #include <pybind11/iostream.h>
 #include <pybind11/numpy.h>
@@ -23,6 +23,33 @@ using Environment = iqs::mpi::Environment;
 using Reg = iqs::QubitRegister<ComplexDP>;
 
 namespace {
+
+// chi matrices of 1- and 2-qubit channels (reference intelqs_py.cpp:94-163): chi[i, j] access,
+// SolveEigenSystem, Print; the B200 module also reads the eigensystem back
+template <unsigned N>
+void BindChi(py::module &m, const char *name, const char *repr) {
+  using Chi = iqs::ChiMatrix<ComplexDP, N, 32>;
+  py::class_<Chi>(m, name)
+      .def(py::init<>())
+      .def("__getitem__", [](const Chi &a, std::pair<py::ssize_t, py::ssize_t> i) {
+        if (i.first < 0 || i.first >= (py::ssize_t)N || i.second < 0 || i.second >= (py::ssize_t)N) throw py::index_error();
+        return a(i.first, i.second);
+      }, py::is_operator())
+      .def("__setitem__", [](Chi &a, std::pair<py::ssize_t, py::ssize_t> i, ComplexDP value) {
+        if (i.first < 0 || i.first >= (py::ssize_t)N || i.second < 0 || i.second >= (py::ssize_t)N) throw py::index_error();
+        a(i.first, i.second) = value;
+      }, py::is_operator())
+      .def("SolveEigenSystem", &Chi::SolveEigenSystem)
+      .def("EigensystemOfIdealHadamardChannel", &Chi::EigensystemOfIdealHadamardChannel)
+      .def("GetEigenValues", &Chi::GetEigenValues, "B200: eigenvalues (ascending)")
+      .def("GetEigenProbabilities", &Chi::GetEigenProbabilities, "B200: |E_k| / sum |E_k|")
+      .def("GetEigenVectors", &Chi::GetEigenVectors, "B200: standardised, renormalised eigenvectors in the Pauli basis")
+      .def("Print", [](Chi &a, bool with_eigensystem) {
+        py::scoped_ostream_redirect stream(std::cout, py::module::import("sys").attr("stdout"));
+        a.Print(with_eigensystem);
+      }, py::arg("with_eigensystem") = true)
+      .def("__repr__", [repr](const Chi &) { return std::string(repr); });
+}
 
 TM2x2<ComplexDP> FromArray(py::array_t<ComplexDP, py::array::c_style | py::array::forcecast> matrix) {
   py::buffer_info buf = matrix.request();
@@ -96,6 +123,9 @@ PYBIND11_MODULE(intelqs_py, m) {
            "Return an array of 'size' random number from the uniform distribution [a,b[.")
       .def("__repr__", [](const iqs::RandomNumberGenerator<double> &) { return "<RandomNumberGenerator (std::mt19937 streams)>"; });
 
+  BindChi<4>(m, "CM4x4", "<ChiMatrix for 1-qubit channel>");
+  BindChi<16>(m, "CM16x16", "<ChiMatrix for 2-qubit channel>");
+
   py::class_<Reg>(m, "QubitRegister", py::buffer_protocol(), py::dynamic_attr())
       .def(py::init<>())
       .def(py::init<const Reg &>())
@@ -147,6 +177,10 @@ PYBIND11_MODULE(intelqs_py, m) {
       }, "Apply custom controlled-1-qubit gate.")
       .def("ApplyToffoli", &Reg::ApplyToffoli)
       .def("GetOverallSignOfChannels", &Reg::GetOverallSignOfChannels)
+      .def("ApplyChannel", [](Reg &a, unsigned qubit, iqs::ChiMatrix<ComplexDP, 4, 32> chi) { a.ApplyChannel(qubit, chi); },
+           "Apply 1-qubit channel provided via its chi-matrix.")
+      .def("ApplyChannel", [](Reg &a, unsigned qubit1, unsigned qubit2, iqs::ChiMatrix<ComplexDP, 16, 32> chi) { a.ApplyChannel(qubit1, qubit2, chi); },
+           "Apply 2-qubit channel provided via its chi-matrix.")
       // state initialization
       .def("Initialize", (void (Reg::*)(std::string, std::size_t)) & Reg::Initialize)
       .def("TurnOnSpecialize", &Reg::TurnOnSpecialize)

@@ -196,3 +196,66 @@ def test_random_state_matches_reference_stream(iqs):
     ref = v[0::2] + 1j * v[1::2]
     ref /= np.linalg.norm(ref)
     assert np.max(np.abs(a - ref)) < 1e-14
+
+
+def test_chi_matrix_binding_and_channels(iqs):
+    """CM4x4 / CM16x16, SolveEigenSystem and ApplyChannel from Python (reference intelqs_py.cpp:94-163,
+    263-271; usage as in notebooks/chi_matrix_with_mpi.py:24-49)."""
+    p = 0.1
+    # amplitude-damping chi of the reference notebook (has a negative eigenvalue)
+    chi = iqs.CM4x4()
+    chi[0, 0] = (1 + np.sqrt(1 - p)) ** 2
+    chi[0, 3] = p
+    chi[3, 0] = p
+    chi[3, 3] = (1 - np.sqrt(1 - p)) ** 2
+    chi[1, 1] = p ** 2
+    chi[1, 2] = -1j * p ** 2
+    chi[2, 1] = +1j * p ** 2
+    chi[2, 2] = p ** 2
+    assert chi[1, 2] == -1j * p ** 2
+    chi.SolveEigenSystem()
+    E = np.array(chi.GetEigenValues()).real
+    W = np.array(chi.GetEigenVectors())  # W[k, i]
+    probs = np.array(chi.GetEigenProbabilities())
+    total = np.abs(E).sum()
+    assert np.all(np.diff(E) >= 0) and abs(probs.sum() - 1) < 1e-14
+    want = np.array([[chi[i, j] for j in range(4)] for i in range(4)])
+    got = sum(E[k] / total * np.outer(W[k], W[k].conj()) for k in range(4))
+    assert np.max(np.abs(got - want)) < 1e-13
+    with pytest.raises(IndexError):
+        chi[4, 0]
+
+    # dephasing rho' = (1-p) rho + p Z rho Z on |+>: every trajectory stays |+> or |->, <X> decays as (1-2p)^t
+    chi = iqs.CM4x4()
+    chi[0, 0] = 1 - p
+    chi[3, 3] = p
+    chi.SolveEigenSystem()
+    rng = iqs.RandomNumberGenerator()
+    rng.SetSeedStreamPtrs(7777)
+    plus = iqs.QubitRegister(3, "base", 0, 0)
+    plus.ApplyHadamard(1)
+    steps, ensemble, mean = 5, 300, 0.0
+    for _ in range(ensemble):
+        psi = iqs.QubitRegister(plus)
+        psi.SetRngPtr(rng)
+        for _t in range(steps):
+            psi.ApplyChannel(1, chi)
+        ov = abs(psi.ComputeOverlap(plus)) ** 2
+        assert min(abs(ov), abs(ov - 1)) < 1e-12 and abs(psi.ComputeNorm() - 1) < 1e-12
+        mean += (2 * ov - 1) / ensemble
+        assert psi.GetOverallSignOfChannels() == 1
+    assert abs(mean - (1 - 2 * p) ** steps) < 0.2
+
+    # two-qubit channel: chi of the ideal CZ = 1/2 (II + IZ + ZI - ZZ) reproduces the gate
+    chi2 = iqs.CM16x16()
+    idx, v = [0, 3, 12, 15], [0.5, 0.5, 0.5, -0.5]
+    for a in range(4):
+        for b in range(4):
+            chi2[idx[a], idx[b]] = v[a] * v[b]
+    chi2.SolveEigenSystem()
+    psi = iqs.QubitRegister(5, "++++", 0, 0)
+    ideal = iqs.QubitRegister(5, "++++", 0, 0)
+    psi.SetRngPtr(rng)
+    psi.ApplyChannel(0, 3, chi2)
+    ideal.ApplyCPauliZ(0, 3)
+    assert abs(abs(ideal.ComputeOverlap(psi)) ** 2 - 1) < 1e-12

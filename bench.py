@@ -402,7 +402,7 @@ def gpu_arm(args, pkg):
                "gates_per_s": job_gates / t_e2e, "api": "intelqs_py.QubitRegister.Apply1QubitGate/ApplyControlled1QubitGate(numpy 2x2) + GetProbability",
                "note": "the state stays resident in HBM like the reference's stays in RAM; per-step host inputs are the gate matrices"}
         # the same steps with gate fusion on (TurnOnFusion): reported next to the headline, not as it
-        try:
+        def fused_leg():
             psi.TurnOnFusion(11)
             api_layer(layers[0], cm[0])
             iqs.MPIEnvironment.StateBarrier()
@@ -415,8 +415,15 @@ def gpu_arm(args, pkg):
             ms_dev = iqs.DeviceTimerStop()
             t_f = all_max(max(time.perf_counter() - t0, ms_dev * 1e-3))
             psi.TurnOffFusion()
-            e2e["fused"] = {"value": job_bytes / t_f / 1e9, "unit": "GB/s", "gates_per_s": job_gates / t_f,
-                            "note": "TurnOnFusion(): runs of gates share one HBM sweep (shared-memory tiles built from arbitrary qubit positions)"}
+            return {"value": job_bytes / t_f / 1e9, "unit": "GB/s", "gates_per_s": job_gates / t_f}
+
+        try:
+            e2e["fused"] = fused_leg()
+            e2e["fused"]["note"] = "TurnOnFusion(): runs of gates share one HBM sweep (shared-memory tiles built from arbitrary qubit positions); exact arithmetic, bit-identical results"
+            iqs.SetContractedArithmetic(True)
+            e2e["fused_fma"] = fused_leg()
+            e2e["fused_fma"]["note"] = "same with IQSB_ARITH_FMA (opt-in, like the reference's IqsNative=ON build): results agree to ~1e-16"
+            iqs.SetContractedArithmetic(False)
         except Exception as exc:
             log(f"[bench] fused leg failed: {exc!r}")
         del psi

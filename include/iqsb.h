@@ -64,6 +64,16 @@ int iqsb_mem_info(iqsb_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes);
  * CUDA events bracket our launches; NULL restores the context's own stream. */
 int iqsb_set_stream(iqsb_ctx *ctx, void *cuda_stream);
 void *iqsb_get_stream(iqsb_ctx *ctx);
+/* Arithmetic of the fused kernel.  IQSB_ARITH_EXACT (default): separately rounded products and
+ * sums in the reference's operation order -- results bit-identical to the reference built for
+ * baseline x86-64.  IQSB_ARITH_FMA: contracted multiply-adds, what the reference's IqsNative=ON
+ * (-march=native) build lets its compiler do (CMakeLists.txt:205-215); results agree to ~1e-16 and
+ * the in-tile phase of iqsb_fused issues 16 instead of 28 FP64 instructions per pair.  The initial
+ * mode comes from the environment variable IQS_B200_ARITH ("exact" | "fma"). */
+#define IQSB_ARITH_EXACT 0
+#define IQSB_ARITH_FMA 1
+int iqsb_set_arith(iqsb_ctx *ctx, int mode);
+int iqsb_get_arith(const iqsb_ctx *ctx);
 /* number of kernels this context launched since creation (bench.py: gpu_launches). */
 uint64_t iqsb_launch_count(const iqsb_ctx *ctx);
 /* device-side timing on the context's stream (CUDA events). */

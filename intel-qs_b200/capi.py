@@ -102,7 +102,7 @@ def load():
         "iqsb_rank": [c_vp], "iqsb_nranks": [c_vp], "iqsb_device": [c_vp],
         "iqsb_sync": [c_vp],
         "iqsb_mem_info": [c_vp, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)],
-        "iqsb_set_stream": [c_vp, c_vp], "iqsb_get_stream": [c_vp],
+        "iqsb_set_stream": [c_vp, c_vp], "iqsb_get_stream": [c_vp], "iqsb_set_arith": [c_vp, c_int], "iqsb_get_arith": [c_vp],
         "iqsb_launch_count": [c_vp], "iqsb_nvlink_bytes": [c_vp],
         "iqsb_timer_start": [c_vp], "iqsb_timer_stop": [c_vp, ctypes.POINTER(c_dbl)],
         "iqsb_event_record": [c_vp, c_int], "iqsb_event_elapsed": [c_vp, c_int, c_int, ctypes.POINTER(c_dbl)],
@@ -217,6 +217,13 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         _chk(self.L.iqsb_set_stream(self.h, c_vp(cuda_stream_ptr)))
+
+    def set_arith(self, fma):
+        """False: exact, reference operation order (default); True: contracted multiply-adds in the fused kernel"""
+        _chk(self.L.iqsb_set_arith(self.h, 1 if fma else 0))
+
+    def get_arith(self):
+        return int(self.L.iqsb_get_arith(self.h))
 
     def launches(self):
         return int(self.L.iqsb_launch_count(self.h))

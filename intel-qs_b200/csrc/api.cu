@@ -67,6 +67,7 @@ extern "C" int iqsb_init(int rank, int nranks, const void *uid, int device, iqsb
   IQSB_CUDA(cudaMalloc(&ctx->d_result, sizeof(double) * kMaxRedOut));
   IQSB_CUDA(cudaMalloc(&ctx->d_flags, sizeof(int) * 4));
   IQSB_CUDA(cudaMallocHost(&ctx->h_result, sizeof(double) * kMaxRedOut));
+  if (const char *a = getenv("IQS_B200_ARITH")) ctx->arith = (strcmp(a, "fma") == 0 || strcmp(a, "FMA") == 0) ? IQSB_ARITH_FMA : IQSB_ARITH_EXACT;
   if (nranks > 1) {
     int rc = iqsb_comm_init(ctx, uid);
     if (rc != IQSB_OK) return rc;
@@ -127,6 +128,14 @@ extern "C" int iqsb_set_stream(iqsb_ctx *ctx, void *cuda_stream) {
   return IQSB_OK;
 }
 extern "C" void *iqsb_get_stream(iqsb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int iqsb_set_arith(iqsb_ctx *ctx, int mode) {
+  IQSB_REQUIRE(ctx, "iqsb_set_arith: null context");
+  IQSB_REQUIRE(mode == IQSB_ARITH_EXACT || mode == IQSB_ARITH_FMA, "iqsb_set_arith: unknown mode %d", mode);
+  ctx->arith = mode;
+  return IQSB_OK;
+}
+extern "C" int iqsb_get_arith(const iqsb_ctx *ctx) { return ctx ? ctx->arith : IQSB_ARITH_EXACT; }
 
 extern "C" int iqsb_timer_start(iqsb_ctx *ctx) {
   IQSB_REQUIRE(ctx, "iqsb_timer_start: null context");

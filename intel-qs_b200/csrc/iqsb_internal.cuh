@@ -65,6 +65,7 @@ struct iqsb_ctx {
   // the same offsets in device memory, consumed in stream order, so no host synchronisation per use
   unsigned char *stage_h = nullptr, *stage_d = nullptr;
   size_t stage_off = 0;
+  int arith = IQSB_ARITH_EXACT;  // iqsb_set_arith
 };
 constexpr size_t kStageBytes = 1u << 20;
 
@@ -137,6 +138,18 @@ __device__ __forceinline__ void apply2x2(const Mat2<T> &m, Cx<T> &a0, Cx<T> &a1)
   Cx<T> in0 = a0, in1 = a1;
   a0 = cadd(cmul(m.m00, in0), cmul(m.m01, in1));
   a1 = cadd(cmul(m.m10, in0), cmul(m.m11, in1));
+}
+
+// The same update with contracted multiply-adds (IQSB_ARITH_FMA): 16 instead of 28 instructions.
+__device__ __forceinline__ double fma_c(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float fma_c(float a, float b, float c) { return fmaf(a, b, c); }
+template <typename T>
+__device__ __forceinline__ void apply2x2_fma(const Mat2<T> &m, Cx<T> &a0, Cx<T> &a1) {
+  const Cx<T> x = a0, y = a1;
+  a0.re = fma_c(m.m00.re, x.re, fma_c(-m.m00.im, x.im, fma_c(m.m01.re, y.re, -m.m01.im * y.im)));
+  a0.im = fma_c(m.m00.re, x.im, fma_c(m.m00.im, x.re, fma_c(m.m01.re, y.im, m.m01.im * y.re)));
+  a1.re = fma_c(m.m10.re, x.re, fma_c(-m.m10.im, x.im, fma_c(m.m11.re, y.re, -m.m11.im * y.im)));
+  a1.im = fma_c(m.m10.re, x.im, fma_c(m.m10.im, x.re, fma_c(m.m11.re, y.im, m.m11.im * y.re)));
 }
 
 // A chunk: two adjacent amplitudes.

@@ -110,7 +110,7 @@ __device__ __forceinline__ void tile_store(const Cx<T> *tile, Chunk<T> *g, const
 
 constexpr int kGateBatch = 16;  // gate descriptors staged in shared memory at a time
 
-template <typename T>
+template <typename T, bool FMA>
 __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
     k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, const FGate<T> *__restrict__ gates, int ngates) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -162,7 +162,8 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
             const unsigned x = (unsigned)insert_zero(j, ts);
             const unsigned i0 = phys(x), i1 = phys(x | (1u << ts));
             Cx<T> a = tile[i0], b = tile[i1];
-            apply2x2(m, a, b);
+            if (FMA) apply2x2_fma(m, a, b);
+            else apply2x2(m, a, b);
             tile[i0] = a;
             tile[i1] = b;
           }
@@ -174,7 +175,8 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
             const unsigned x = (unsigned)insert_zero(insert_zero(j, lo), hi) | (1u << cs);
             const unsigned i0 = phys(x), i1 = phys(x | (1u << ts));
             Cx<T> a = tile[i0], b = tile[i1];
-            apply2x2(m, a, b);
+            if (FMA) apply2x2_fma(m, a, b);
+            else apply2x2(m, a, b);
             tile[i0] = a;
             tile[i1] = b;
           }
@@ -228,14 +230,15 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, int first, int last, const 
   IQSB_CUDA(cudaMemcpyAsync(d, ctx->stage_h + ctx->stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stage_off += (bytes + 255) & ~(size_t)255;
   size_t smem = (size_t)sizeof(Cx<T>) << td.nS;
-  IQSB_CUDA(cudaFuncSetAttribute(k_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kernel = ctx->arith == IQSB_ARITH_FMA ? k_fused<T, true> : k_fused<T, false>;
+  IQSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
-  IQSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<T>, kThreads, smem));
+  IQSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
   if (per_sm < 1) per_sm = 1;
   uint64_t nouter = st->local_amps >> td.nS;
   uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
   unsigned grid = (unsigned)(nouter < cap ? nouter : cap);
-  k_fused<T><<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, (int)gates.size());
+  kernel<<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, (int)gates.size());
   return iqsb_check_launch(ctx, "k_fused");
 }
 

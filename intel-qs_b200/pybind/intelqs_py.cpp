@@ -99,6 +99,9 @@ PYBIND11_MODULE(intelqs_py, m) {
     if (nranks > 1 && s.size() != IQSB_UNIQUE_ID_BYTES) throw std::runtime_error("the unique id must be 128 bytes");
     Environment::InitWithUniqueId(rank, nranks, nranks > 1 ? s.data() : nullptr, device);
   }, py::arg("rank"), py::arg("nranks"), py::arg("uid"), py::arg("device") = -1);
+  m.def("SetContractedArithmetic", [](bool fma) {
+    if (iqsb_set_arith(Environment::Context(), fma ? IQSB_ARITH_FMA : IQSB_ARITH_EXACT) != IQSB_OK) throw std::runtime_error(iqsb_last_error());
+  }, "B200: False (default) = exact arithmetic in the reference's operation order; True = contracted multiply-adds in the fused kernel");
   m.def("LaunchCount", []() { return (unsigned long long)iqsb_launch_count(Environment::Context()); }, "B200: kernels launched so far");
   m.def("NvlinkBytes", []() { return (unsigned long long)iqsb_nvlink_bytes(Environment::Context()); }, "B200: bytes moved over NVLink so far");
   m.def("DeviceTimerStart", []() { iqsb_timer_start(Environment::Context()); }, "B200: CUDA event on the engine's stream");

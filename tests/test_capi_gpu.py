@@ -349,6 +349,41 @@ def test_fused_matches_sequential(gpu_ctx, oracle):
     st.free()
 
 
+def test_fused_contracted_arithmetic_mode(gpu_ctx, oracle):
+    """IQSB_ARITH_FMA (opt-in, the reference's IqsNative=ON analogue): same result to rounding, not
+    bit for bit; the default mode is restored and stays exact."""
+    n = 14
+    st = gpu_ctx.alloc(1 << n)
+    psi = C.random_state(n, seed=77)
+    rng = np.random.Generator(np.random.MT19937(5))
+    ref = psi.copy()
+    gates = []
+    for i in range(60):
+        m = np.ascontiguousarray(random_unitary(rng)).ravel().view(np.float64).copy()
+        t, c = (int(x) for x in rng.permutation(n)[:2])
+        if i % 2:
+            gates.append((0, 0, t, m))
+            oracle.gate1(ref, t, m)
+        else:
+            gates.append((1, c, t, m))
+            oracle.cgate1(ref, c, t, m)
+    assert gpu_ctx.get_arith() == 0
+    try:
+        gpu_ctx.set_arith(True)
+        st.upload(psi)
+        st.fused(gates)
+        got = st.download()
+    finally:
+        gpu_ctx.set_arith(False)
+    err = np.max(np.abs(got - ref))
+    assert err < 1e-14, err  # amplitudes ~ 2^-7, 60 gates: a few ulp
+    assert abs(st.norm2() - 1.0) < 1e-13
+    st.upload(psi)
+    st.fused(gates)
+    assert np.array_equal(st.download(), ref)  # exact mode again
+    st.free()
+
+
 def test_small_fused_tiles(gpu_ctx, oracle):
     for n in (2, 3, 5):
         st = gpu_ctx.alloc(1 << n)

@@ -33,12 +33,14 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--mem", default="device")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--arith", default="exact", choices=["exact", "fma"], help="arithmetic of the fused kernel (iqsb_set_arith)")
     ap.add_argument("--ops", default="gate1,cgate1,swap,diag,phase,prob,norm,parity,fused,gate2,collapse,permute")
     a = ap.parse_args()
     n = a.n
     L = 1 << n
     peak, how = peak_gbs()
     ctx = capi.Context()
+    ctx.set_arith(a.arith == "fma")
     st = ctx.alloc(L, mem=capi.MEM_MANAGED if a.mem == "managed" else capi.MEM_DEVICE)
     st.fill_random(1)
     st.scale(1.0 / math.sqrt(st.norm2()))

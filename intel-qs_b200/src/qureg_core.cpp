@@ -257,6 +257,13 @@ void QubitRegister<Type>::Allocate(std::size_t new_num_qubits, std::size_t tmp_s
            iqs::mpi::Environment::GetStateSize() > 1 ? double(TmpSize()) * sizeof(Type) / MB : 0.0);
   }
   AllocateDevice();
+  // IQS_B200_AUTO_FUSION=1: registers start with fusion on, as if TurnOnFusion() had been called --
+  // unchanged programs get one HBM sweep per run of gates; results are bit-identical, reads flush.
+  if (const char *e = getenv("IQS_B200_AUTO_FUSION"))
+    if (e[0] == '1' && LocalQubits() >= 2) {
+      log2llc = LocalQubits();
+      fusion = true;
+    }
 }
 
 template <class Type>

@@ -70,6 +70,27 @@ def test_fusion_matches_unfused_reference_semantics(oracle):
         assert np.array_equal(got["state"], want), f"log2llc={log2llc}: {np.max(np.abs(got['state'] - want))}"
 
 
+def test_auto_fusion_env_is_transparent(oracle):
+    """IQS_B200_AUTO_FUSION=1: an unchanged program (every op kind, permutations, reductions,
+    collapse) runs with registers that fuse from the start; states, scalars and maps are the same."""
+    n, seed = 13, 41
+    rng = np.random.default_rng(seed)
+    prog = random_program(n, 250, seed)
+    prog.permute(list(rng.permutation(n)))
+    prog.extend(random_program(n, 150, seed + 1))
+    for q in (0, 5, n - 1):
+        prog.prob(q)
+    prog.expect([0, 1, 2], [1, 2, 3]).norm()
+    prog.collapse(2, 0).norm()  # (no Normalize: its scalar comes from a reduction whose summation order differs)
+    prog.extend(random_program(n, 60, seed + 2))
+    psi = C.random_state(n, seed)
+    want, wsc, wmap = oracle.run_program(n, psi, prog.ops)
+    got = run_gpu(oracle, prog, state=psi, extra_env={"IQS_B200_AUTO_FUSION": "1"})
+    assert np.array_equal(got["map"], wmap)
+    assert np.max(np.abs(got["scalars"] - wsc)) <= TOL
+    assert np.array_equal(got["state"], want)
+
+
 def test_spec_modes_do_not_change_results(oracle):
     n = 10
     base = random_program(n, 200, 7)

@@ -5,9 +5,9 @@
 // block by block, with blocks of 2^log2llc CONTIGUOUS amplitudes sized for the CPU's last-level
 // cache -- so only gates whose target lies below log2llc can be fused there.
 //
-// Here a tile is the set of 2^K amplitudes (K = 11: 32 KiB of ComplexDP) whose indices differ only
+// Here a tile is the set of 2^K amplitudes (K = 12: 64 KiB of ComplexDP) whose indices differ only
 // in K chosen bit positions pos[0] < pos[1] < ...: the four lowest positions are always part of it
-// (global accesses are 256-byte runs, moved as 32-byte chunks), the other seven are whatever
+// (global accesses are 256-byte runs, moved as 32-byte chunks), the other eight are whatever
 // positions the gates of the run act on.  A run of consecutive gates whose targets fit in one tile
 // costs ONE read and ONE write of the state, wherever the target qubits sit; iqsb_fused cuts a
 // batch into such runs greedily.  Controls may be anywhere: inside the tile they are a bit of the
@@ -16,9 +16,10 @@
 //
 // Inside a tile every gate is one shared-memory round trip of the tile (16-byte slots, XOR-swizzled
 // so that the 8 lanes of a quarter-warp hit 8 different bank groups for every target slot).
-// Measured (profiles/): short runs are HBM-bound; beyond ~4 gates per run the shared-memory
-// bandwidth (~78 %) and the FP64 issue rate of the exact, non-contracted arithmetic (28 operations
-// per pair) bound the kernel at ~1.4 ms per gate for 2^30 amplitudes, 3.5x cheaper than a sweep.
+// Measured (profiles/r01_ncu_summary.md): a run costs one sweep (78-91 % of the copy peak) plus
+// 1.36 ms per gate per 2^30 amplitudes inside the tile, 3.5x cheaper than a sweep per gate; that
+// in-tile cost is bound by the FP64 issue rate of the exact, non-contracted arithmetic (28
+// instructions per pair), 1.05 ms with IQSB_ARITH_FMA (16 instructions, then shared-memory bound).
 #include <string.h>
 
 #include <vector>

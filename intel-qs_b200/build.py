@@ -100,6 +100,12 @@ def build_driver(verbose=False):
                                   "-o", exe, src, "-L" + LIB, "-liqs", "-liqs_b200", "-Wl,-rpath,$ORIGIN/../lib"])
     if verbose:
         print(f"[build] {exe}")
+    # the pool-of-states scenario (tests/pool_check.cpp), launched by tests/test_multigpu.py
+    pool_src = os.path.join(ROOT, "tests", "pool_check.cpp")
+    pool_exe = os.path.join(BIN, "pool_check")
+    if os.path.exists(pool_src) and _newer(pool_exe, [pool_src, os.path.join(LIB, "libiqs.so")] + glob.glob(os.path.join(HERE, "include", "*.hpp"))):
+        _run([CXX] + CXX_FLAGS + ["-I" + os.path.join(HERE, "include"), "-I" + os.path.join(ROOT, "include"), "-o", pool_exe, pool_src,
+                                  "-L" + LIB, "-liqs", "-liqs_b200", "-Wl,-rpath,$ORIGIN/../lib"])
     return exe
 
 

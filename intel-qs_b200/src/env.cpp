@@ -61,7 +61,7 @@ bool Environment::is_verbose = true;
 
 namespace {
 iqsb_ctx *g_ctx = nullptr;
-int g_rank = 0, g_size = 1;
+int g_rank = 0, g_size = 1, g_num_states = 1;
 bool g_finalized = false;
 
 [[noreturn]] void die(const char *what) {
@@ -184,64 +184,87 @@ void Environment::Finalize() {
     iqsb_finalize(g_ctx);
     g_ctx = nullptr;
     g_finalized = false;  // a later Init() may start a new context
+    g_num_states = 1;
   }
 }
 
+// Pool of states (reference src/mpi_env.cpp:279-360): the useful ranks are split into num_states
+// groups, each holding one state.  Two splits are supported: one state over all GPUs (the default,
+// the hot path) and one state PER GPU -- what the noisy-simulation tutorials and examples use to run
+// an ensemble of trajectories in parallel.  Then every register is a single-GPU register (no
+// global qubits, no exchange), and only IncoherentSumOverAllStatesOfPool crosses GPUs.
+// Intermediate splits would need one NCCL communicator and peer table per group: not provided.
 void Environment::UpdateStateComm(int new_num_states) {
-  if (new_num_states != 1)
-    throw std::runtime_error("iqs::mpi::Environment::UpdateStateComm: pools of several states run as independent replicas on this engine (num_states must be 1)");
+  if (new_num_states == 1 || new_num_states == g_size) {
+    if (g_ctx) iqsb_sync(g_ctx);
+    g_num_states = new_num_states;
+    return;
+  }
+  throw std::runtime_error("iqs::mpi::Environment::UpdateStateComm: supported pools are 1 state over all " + std::to_string(g_size) +
+                           " GPUs or one state per GPU; got num_states = " + std::to_string(new_num_states));
 }
 
 int Environment::GetPoolRank() { return g_rank; }
-int Environment::GetStateRank() { return g_rank; }
 int Environment::GetPoolSize() { return g_size; }
-int Environment::GetStateSize() { return g_size; }
+int Environment::GetStateRank() { return g_num_states == 1 ? g_rank : 0; }
+int Environment::GetStateSize() { return g_num_states == 1 ? g_size : 1; }
 int Environment::GetNumRanksPerNode() { return g_size; }
 int Environment::GetNumNodes() { return 1; }
 int Environment::GetNodeId() { return 0; }
-int Environment::GetStateId() { return 0; }
-int Environment::GetNumStates() { return 1; }
+int Environment::GetStateId() { return g_num_states == 1 ? 0 : g_rank; }
+int Environment::GetNumStates() { return g_num_states; }
 // The reference renumbers ranks to implement X/Y on a global qubit without data movement
 // (spec-v1 only, flagged buggy: qureg_apply1qubitgate.cpp:61-99).  Not used by this engine.
 void Environment::RemapStateRank(int) {}
 
+// sum over the pool divided by the ranks per state (mpi_env.cpp:467-486): every rank of a state
+// holds the same value, so this is the sum over states
 template <class Type>
 Type Environment::IncoherentSumOverAllStatesOfPool(Type local_value) {
-  return local_value;  // one state in the pool
+  if (g_size == 1) return local_value;
+  double v = (double)local_value;
+  if (iqsb_allreduce_f64(Environment::Context(), &v, 1, IQSB_SUM) != IQSB_OK) die("allreduce over the pool failed");
+  return (Type)(v / double(GetStateSize()));
 }
 template float Environment::IncoherentSumOverAllStatesOfPool<float>(float);
 template double Environment::IncoherentSumOverAllStatesOfPool<double>(double);
 
 // Barriers also drain the engine's stream: after StateBarrier() the host may read managed state.
-void StateBarrier() {
+void PoolBarrier() {
   if (g_ctx && iqsb_barrier(g_ctx) != IQSB_OK) die("barrier failed");
 }
-void PoolBarrier() { StateBarrier(); }
-void Barrier() { StateBarrier(); }
+void StateBarrier() {
+  if (Environment::GetStateSize() > 1) PoolBarrier();
+  else if (g_ctx && iqsb_sync(g_ctx) != IQSB_OK) die("synchronisation failed");
+}
+void Barrier() { PoolBarrier(); }
 
-void StatePrint(std::string s, bool all) {
-  int rank = Environment::GetStateRank(), size = Environment::GetStateSize();
+namespace {
+void PrintInOrder(const std::string &s, bool all, int rank, int size, void (*barrier)()) {
   if (all) {
     for (int r = 0; r < size; ++r) {
       if (r == rank) {
         printf("[|%d>:%3d] %s\n", Environment::GetStateId(), rank, s.c_str());
         fflush(stdout);
       }
-      StateBarrier();
+      barrier();
     }
   } else if (rank == 0) {
     std::cout << s << std::endl;
   }
 }
-void PoolPrint(std::string s, bool all) { StatePrint(s, all); }
-void Print(std::string s, bool all) { StatePrint(s, all); }
+}  // namespace
+void StatePrint(std::string s, bool all) { PrintInOrder(s, all, Environment::GetStateRank(), Environment::GetStateSize(), StateBarrier); }
+void PoolPrint(std::string s, bool all) { PrintInOrder(s, all, Environment::GetPoolRank(), Environment::GetPoolSize(), PoolBarrier); }
+void Print(std::string s, bool all) { PoolPrint(s, all); }
 
+// collectives of ONE state: nothing to do when the state lives on one GPU
 void AllreduceDouble(double *inout, int n, ReduceOp op) {
-  if (g_size == 1) return;
+  if (Environment::GetStateSize() == 1) return;
   if (iqsb_allreduce_f64(Environment::Context(), inout, n, op == MAX ? IQSB_MAX : IQSB_SUM) != IQSB_OK) die("allreduce failed");
 }
 void BcastDouble(double *inout, int n, int root) {
-  if (g_size == 1) return;
+  if (Environment::GetStateSize() == 1) return;
   if (iqsb_bcast_f64(Environment::Context(), inout, n, root) != IQSB_OK) die("broadcast failed");
 }
 

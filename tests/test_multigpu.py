@@ -124,3 +124,17 @@ def test_two_qubit_gate_on_global_qubits(oracle, nranks):
     want, _, _ = oracle.run_program(n, psi, prog.ops)
     got = run_ranks(oracle, nranks, prog, state=psi)
     assert np.array_equal(got["state"], want)
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_pool_of_states_one_state_per_gpu(nranks):
+    """iqs::mpi::Environment::UpdateStateComm(num_states = number of GPUs): an ensemble of noisy
+    trajectories, one single-GPU state per rank, IncoherentSumOverAllStatesOfPool across them
+    (reference noisy_simulation_test.hpp:52-158) -- tests/pool_check.cpp under tools/iqsrun."""
+    need(nranks)
+    exe = os.path.join(ROOT, "intel-qs_b200", "bin", "pool_check")
+    assert os.path.exists(exe), "intel-qs_b200/bin/pool_check is missing: run __graft_entry__.build()"
+    r = subprocess.run([sys.executable, IQSRUN, "-n", str(nranks), "--timeout", "300", exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "ALL OK" in r.stdout and "FAILED" not in r.stdout
+    assert "OK one_state_at_a_time" in r.stdout and "OK one_state_per_rank" in r.stdout

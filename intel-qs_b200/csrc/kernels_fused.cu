@@ -33,7 +33,7 @@ namespace {
 #define IQSB_FUSED_THREADS 256
 #endif
 #ifndef IQSB_FUSED_MINBLOCKS
-#define IQSB_FUSED_MINBLOCKS 3
+#define IQSB_FUSED_MINBLOCKS 4
 #endif
 #ifndef IQSB_FUSED_TILE
 #define IQSB_FUSED_TILE 12
@@ -42,7 +42,10 @@ namespace {
 #define IQSB_FUSED_LOW 4
 #endif
 #ifndef IQSB_FUSED_LOADS
-#define IQSB_FUSED_LOADS 4
+#define IQSB_FUSED_LOADS 2
+#endif
+#ifndef IQSB_FUSED_ASYNC_LOAD
+#define IQSB_FUSED_ASYNC_LOAD 1
 #endif
 #ifndef IQSB_FUSED_PAIR_UNROLL
 #define IQSB_FUSED_PAIR_UNROLL 2
@@ -70,6 +73,31 @@ struct TileDesc {
 
 // 16-byte slots; swizzle so that pairs (i, i + 2^s) are conflict free for every s
 __device__ __forceinline__ unsigned phys(unsigned i) { return i ^ (((i >> 3) & 1u) * 7u); }
+
+// global -> tile without register staging: one asynchronous 16-byte (ComplexDP) / 8-byte (ComplexSP)
+// copy per amplitude, straight into its swizzled slot (LDGSTS).  Every thread has its whole share
+// of the tile in flight at once, which is what brings the sweep of a run to the copy bandwidth
+// (profiles/r01_ncu_summary.md: 8 x 32 B per thread in one batch = 101 % of the copy peak, but 64
+// staging registers cost a CTA per SM; the asynchronous copies need none).
+__device__ __forceinline__ void cp_async_amp(Cx<double> *smem, const Cx<double> *gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_amp(Cx<float> *smem, const Cx<float> *gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void tile_load_async(Cx<T> *tile, const Chunk<T> *g, const uint64_t *g_lo, const uint64_t *g_hi, unsigned nchunks) {
+#pragma unroll 4
+  for (unsigned c = threadIdx.x; c < nchunks; c += kThreads) {
+    const Cx<T> *src = reinterpret_cast<const Cx<T> *>(g + (g_lo[c & 255] | g_hi[c >> 8]));
+    cp_async_amp(tile + phys(2 * c), src);
+    cp_async_amp(tile + phys(2 * c + 1), src + 1);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 
 // global <-> tile, U 32-byte accesses in flight per thread; nchunks is a multiple of kThreads * U
 template <typename T, int U>
@@ -140,8 +168,12 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
 #pragma unroll 1
     for (int k = 0; k < nS; ++k) base = insert_zero(base, (unsigned)s_pos[k]);
     Chunk<T> *g = state + (base >> 1);
+#if IQSB_FUSED_ASYNC_LOAD
+    tile_load_async<T>(tile, g, g_lo, g_hi, nchunks);
+#else
     if (nchunks % (kThreads * U) == 0) tile_load<T, U>(tile, g, g_lo, g_hi, nchunks);
     else tile_load<T, 1>(tile, g, g_lo, g_hi, nchunks);
+#endif
     for (int g0 = 0; g0 < ngates; g0 += kGateBatch) {
       // stage the next descriptors (the barrier also orders the tile accesses of the previous gate)
       const int nb = ngates - g0 < kGateBatch ? ngates - g0 : kGateBatch;

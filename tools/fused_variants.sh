@@ -5,14 +5,12 @@ set -e
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()" >/dev/null
 variants=(
-  "mb2u1:-DIQSB_FUSED_MINBLOCKS=2 -DIQSB_FUSED_PAIR_UNROLL=1"
-  "mb2u2:-DIQSB_FUSED_MINBLOCKS=2 -DIQSB_FUSED_PAIR_UNROLL=2"
-  "mb3u1:-DIQSB_FUSED_MINBLOCKS=3 -DIQSB_FUSED_PAIR_UNROLL=1"
-  "mb3u2:-DIQSB_FUSED_MINBLOCKS=3 -DIQSB_FUSED_PAIR_UNROLL=2"
-  "mb4u1:-DIQSB_FUSED_MINBLOCKS=4 -DIQSB_FUSED_PAIR_UNROLL=1"
-  "t12mb2u1:-DIQSB_FUSED_TILE=12 -DIQSB_FUSED_MINBLOCKS=2 -DIQSB_FUSED_PAIR_UNROLL=1"
-  "t12mb3u1:-DIQSB_FUSED_TILE=12 -DIQSB_FUSED_MINBLOCKS=3 -DIQSB_FUSED_PAIR_UNROLL=1"
-  "t12th512:-DIQSB_FUSED_TILE=12 -DIQSB_FUSED_THREADS=512 -DIQSB_FUSED_MINBLOCKS=1 -DIQSB_FUSED_PAIR_UNROLL=1"
+  "sync:-DIQSB_FUSED_ASYNC_LOAD=0"
+  "async:"
+  "async_l2:-DIQSB_FUSED_LOADS=2"
+  "async_mb4:-DIQSB_FUSED_MINBLOCKS=4 -DIQSB_FUSED_LOADS=2"
+  "async_t11mb4:-DIQSB_FUSED_TILE=11 -DIQSB_FUSED_MINBLOCKS=4"
+  "async_t11mb5:-DIQSB_FUSED_TILE=11 -DIQSB_FUSED_MINBLOCKS=5 -DIQSB_FUSED_LOADS=2"
 )
 for v in "${variants[@]}"; do
   name=${v%%:*}; flags=${v#*:}

@@ -30,7 +30,7 @@ GATE1, CGATE1, SWAPLIKE, DIAG, GATE2, TOFFOLI = 1, 2, 3, 4, 5, 6
 H, X, Y, Z, SQRTX, SQRTY, SQRTZ, T, RX, RY, RZ, RXY = 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21
 CH, CX, CY, CZ, CSQRTZ, CRX, CRY, CRZ, CPHASE = 30, 31, 32, 33, 34, 35, 36, 37, 38
 SWAP, ISWAP, SQRTISWAP, FOURTHROOTISWAP = 40, 41, 42, 43
-PROB, EXPECT, NORM, NORMALIZE, COLLAPSE, EXPECT1 = 50, 51, 52, 53, 54, 55
+PROB, EXPECT, NORM, NORMALIZE, COLLAPSE, EXPECT1, ENTROPY, GOOGLESTATS, GETAMP = 50, 51, 52, 53, 54, 55, 56, 57, 58
 PERMUTE, EMUSWAP = 60, 61
 FUSION_ON, FUSION_OFF, SPEC_ON, SPEC_OFF, SPEC2_ON, SPEC2_OFF = 70, 71, 72, 73, 74, 75
 
@@ -99,6 +99,16 @@ class Program:
 
     def norm(self):
         return self._add(NORM)
+
+    def entropy(self):
+        return self._add(ENTROPY)
+
+    def google_stats(self):
+        return self._add(GOOGLESTATS)
+
+    def get_amp(self, global_index):
+        assert 0 <= int(global_index) < (1 << 53)
+        return self._add(GETAMP, p=[float(int(global_index))])
 
     def normalize(self):
         return self._add(NORMALIZE)

@@ -96,6 +96,18 @@ static void run_ops(Reg &psi, const std::vector<iqs_op> &ops, std::vector<double
         else scalars.push_back(psi.ExpectationValueZ(op.q0, 1.));
         break;
       case OP_NORM: scalars.push_back(psi.ComputeNorm()); break;
+      case OP_ENTROPY: scalars.push_back(psi.Entropy()); break;
+      case OP_GOOGLESTATS: {
+        std::vector<double> st = psi.GoogleStats();
+        scalars.insert(scalars.end(), st.begin(), st.end());
+        break;
+      }
+      case OP_GETAMP: {
+        ComplexDP a = psi.GetGlobalAmplitude((std::size_t)op.p[0]);
+        scalars.push_back(a.real());
+        scalars.push_back(a.imag());
+        break;
+      }
       case OP_NORMALIZE: psi.Normalize(); break;
       case OP_COLLAPSE: psi.CollapseQubit(op.q0, op.q1 != 0); break;
       case OP_PERMUTE: {

@@ -379,6 +379,27 @@ static double expect(oreg *r, int k, const double *qs, const double *obs) { /* e
   return v;
 }
 
+/* Entropy() and GoogleStats() (qureg_utils.cpp:305-450): out[0] = entropy in bits, out[1] = average
+ * self-information / 2^n, out[2..10] = moments m_k * 2^(n(k-1)) / k!, k = 2..10. */
+void oracle_google_stats(const cx *state, uint64_t L, double out[11]) {
+  double entropy = 0, avgselfinfo = 0, m[9] = {0};
+  for (uint64_t i = 0; i < L; ++i) {
+    double pj = state[i].re * state[i].re + state[i].im * state[i].im;
+    if (pj != 0.) { double nl = log(pj); entropy -= pj * nl; avgselfinfo -= nl; }
+    double pj2 = pj * pj, pj3 = pj2 * pj, pj4 = pj2 * pj2, pj5 = pj3 * pj2, pj6 = pj3 * pj3, pj7 = pj4 * pj3, pj8 = pj4 * pj4,
+           pj9 = pj5 * pj4, pj10 = pj5 * pj5;
+    m[0] += pj2; m[1] += pj3; m[2] += pj4; m[3] += pj5; m[4] += pj6; m[5] += pj7; m[6] += pj8; m[7] += pj9; m[8] += pj10;
+  }
+  double two2n = (double)L, factorial = 1.0;
+  out[0] = entropy / log(2.0);
+  out[1] = avgselfinfo / log(2.0) / two2n;
+  for (int i = 0; i < 9; ++i) {
+    int k = i + 2;
+    factorial *= (double)k;
+    out[2 + i] = m[i] * (pow(two2n, (double)(k - 1)) / factorial);
+  }
+}
+
 /* Run a program on `state` (2^n amplitudes, interleaved). Scalars produced by value-returning
  * ops are appended to scalars[]; returns their count, or -1 on an unknown op.  map_out (n
  * entries) receives the final qubit->position map. */
@@ -430,6 +451,20 @@ int oracle_run(unsigned n, double *state, const iqs_op *ops, int nops, double *s
       case OP_EXPECT: out = expect(&r, op->q0, op->p, op->p + 16); has_out = 1; break;
       case OP_EXPECT1: out = expect1(&r, op->q0, op->q1); has_out = 1; break;
       case OP_NORM: out = sqrt(oracle_norm2(r.state, L)); has_out = 1; break;
+      case OP_ENTROPY: case OP_GOOGLESTATS: { /* qureg_utils.cpp:305-450: serial sums in index order */
+        if (r.fusion) flush_fused(&r);
+        double st[11];
+        oracle_google_stats(r.state, L, st);
+        int cnt = op->kind == OP_ENTROPY ? 1 : 11;
+        for (int i = 0; i < cnt; ++i) { if (ns < cap) scalars[ns] = st[i]; ++ns; }
+        break; }
+      case OP_GETAMP: { /* qureg_utils.cpp:84-98 with permutation.hpp program2data_ */
+        if (r.fusion) flush_fused(&r);
+        uint64_t gi = (uint64_t)op->p[0], di = 0;
+        for (unsigned q = 0; q < n; ++q) if ((gi >> q) & 1ull) di |= 1ull << r.map[q];
+        if (ns < cap) scalars[ns] = r.state[di].re; ++ns;
+        if (ns < cap) scalars[ns] = r.state[di].im; ++ns;
+        break; }
       case OP_NORMALIZE: { /* qureg_utils.cpp:162-168, 188-196 */
         double nrm = sqrt(oracle_norm2(r.state, L));
         cx f = {1 / nrm, 0};

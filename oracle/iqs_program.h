@@ -44,6 +44,9 @@ enum {
   OP_NORMALIZE = 53, /* Normalize()                                          */
   OP_COLLAPSE = 54,  /* CollapseQubit(q0, q1 != 0)                           */
   OP_EXPECT1 = 55,   /* ExpectationValueX/Y/Z(q0), observable q1 in 1..3     */
+  OP_ENTROPY = 56,     /* Entropy(): one scalar (src/qureg_utils.cpp:305-345)  */
+  OP_GOOGLESTATS = 57, /* GoogleStats(): eleven scalars (:350-450)             */
+  OP_GETAMP = 58,      /* GetGlobalAmplitude(index = p[0], exact below 2^53): two scalars (re, im) */
   /* qubit order */
   OP_PERMUTE = 60,  /* PermuteQubits(map = p[0..n-1], "direct")              */
   OP_EMUSWAP = 61,  /* EmulateSwap(q0, q1)                                   */

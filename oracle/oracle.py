@@ -162,7 +162,7 @@ def run_program(n, state, ops):
     s = np.array(state, dtype=np.complex128, copy=True)
     assert s.size == 1 << n
     ops = np.ascontiguousarray(ops)
-    cap = max(16, len(ops))
+    cap = 16 + 11 * len(ops)
     scal = np.zeros(cap)
     qmap = np.zeros(n, dtype=np.uint64)
     ns = lib().oracle_run(n, s.ctypes.data_as(ctypes.c_void_p), ops.ctypes.data_as(ctypes.c_void_p), len(ops),

@@ -138,3 +138,32 @@ def test_pool_of_states_one_state_per_gpu(nranks):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "ALL OK" in r.stdout and "FAILED" not in r.stdout
     assert "OK one_state_at_a_time" in r.stdout and "OK one_state_per_rank" in r.stdout
+
+
+def _free_gib_per_gpu():
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=memory.free", "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout
+        return min(float(x) for x in out.split()) / 1024.0
+    except Exception:
+        return 0.0
+
+
+@pytest.mark.parametrize("nranks,n", [(2, 20), (4, 21), (8, 22), (2, 33), (4, 34), (8, 35)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_closed_form_amplitudes_sharded(oracle, nranks, n, fused):
+    """An independent answer at sizes no CPU reference holds (35 qubits on 8 GPUs = BASELINE configs[3]
+    size): tests/closed_form.py -- product state, CNOT chain, controlled phases -- with sampled
+    GetGlobalAmplitude reads that force every global bit, against the analytic formula at 1e-12."""
+    need(nranks)
+    M = n - int(np.log2(nranks))
+    if M >= 30 and _free_gib_per_gpu() < (16 * (1 << M) >> 30) + 4:
+        pytest.skip(f"needs {(16 * (1 << M) >> 30) + 4} GiB free per GPU")
+    from closed_form import ClosedForm
+
+    cf = ClosedForm(n, seed=100 + n)
+    samples = cf.samples(10000 if M >= 30 else 2000)
+    got = run_ranks(oracle, nranks, cf.program(C, samples, fused=fused), init=1, base_index=0, want_state=False)
+    sc = got["scalars"]
+    assert sc.size == 2 * len(samples)
+    err, scale = cf.check(samples, sc[0::2] + 1j * sc[1::2], TOL)
+    print(f"closed form {n} qubits on {nranks} GPUs fused={fused}: {len(samples)} amplitudes, max |d| = {err:.3e} (largest |amp| {scale:.3e}), {got['seconds']:.2f} s")

@@ -144,3 +144,40 @@ def test_live_against_compiled_reference(oracle):
         s, sc, m = oracle.run_program(n, psi, prog.ops)
         r = oracle.run_reference(prog, state=psi, threads=1)
         assert np.array_equal(m, r["map"]) and np.array_equal(s, r["state"]) and np.array_equal(sc, r["scalars"])
+
+
+def test_stats_and_amplitude_ops_against_compiled_reference(oracle):
+    """Entropy / GoogleStats / GetGlobalAmplitude (qureg_utils.cpp:84-98, 305-450) under a permuted
+    qubit order: the oracle's restatement vs the reference build (single thread: same summation order)."""
+    if not oracle.have_ref_driver():
+        pytest.skip("oracle/_ref not built on this machine")
+    n, seed = 9, 44
+    prog = random_program(n, 120, seed)
+    prog.permute(list(np.random.default_rng(seed).permutation(n)))
+    prog.extend(random_program(n, 30, seed + 1))
+    prog.entropy().google_stats()
+    for j in (0, 1, 5, 255, 256, 300, 511):
+        prog.get_amp(j)
+    prog.named1(C.H, 2).collapse(2, 0).normalize().entropy().google_stats()
+    psi = C.random_state(n, seed)
+    s, sc, m = oracle.run_program(n, psi, prog.ops)
+    r = oracle.run_reference(prog, state=psi, threads=1)
+    assert sc.size == r["scalars"].size == 12 + 14 + 12
+    assert np.array_equal(s, r["state"]) and np.array_equal(m, r["map"])
+    assert np.all(np.abs(sc - r["scalars"]) <= 1e-13 * np.maximum(1.0, np.abs(sc))), (sc, r["scalars"])
+
+
+def test_closed_form_helper_matches_oracle(oracle):
+    """tests/closed_form.py (the independent answer used at 30-35 qubits) agrees with the oracle at a
+    size the oracle can run, for every amplitude."""
+    from closed_form import ClosedForm
+
+    n = 11
+    cf = ClosedForm(n, seed=3)
+    prog = cf.program(C, [])
+    s, _, _ = oracle.run_program(n, basis(n, 0), prog.ops)
+    idx = list(range(1 << n))
+    cf.check(idx, s, 1e-13)
+    fused = cf.program(C, [5, 77, 2047], fused=True)
+    s2, sc, _ = oracle.run_program(n, basis(n, 0), fused.ops)
+    assert np.array_equal(s2, s) and np.array_equal(sc[0::2] + 1j * sc[1::2], s[[5, 77, 2047]])

@@ -239,6 +239,47 @@ int iqsb_gate1_global(iqsb_state *st, unsigned M, unsigned pos, const double m[8
 int iqsb_cgate1_global(iqsb_state *st, unsigned M, unsigned cpos, unsigned tpos, const double m[8]);
 /* swap-family gate with pos1 < pos2, pos2 >= M: replaces HP_DistrSwap (src/qureg_applyswap.cpp:247-480) */
 int iqsb_swap2x2_global(iqsb_state *st, unsigned M, unsigned pos1, unsigned pos2, const double m[8]);
+/* Exchange the contents of k (1..3) local positions with k global positions in ONE pass: afterwards
+ * the qubit that lived at local position lpos[j] lives at global position gpos[j] and vice versa.
+ * Pure data movement (bit-exact).  Generalises HP_DistrSwap with m = X (src/qureg_applyswap.cpp:247-480)
+ * and replaces the pair-by-pair loop of PermuteByLocalGlobalExchangeOfQubitPairs
+ * (src/qureg_permute.cpp:191-229).  NVLink traffic per rank and direction: (1 - 2^-k) * 16 B * local_amps.
+ * Needs M >= k + 1.  This is what the host library's placement layer uses to bring a global qubit
+ * in once and keep it local for the gates that follow. */
+int iqsb_exchange_bits(iqsb_state *st, unsigned M, int k, const unsigned *lpos, const unsigned *gpos);
+/* Pure host function (no GPU needed): what THIS rank moves in iqsb_exchange_bits.  For partner p the
+ * rank trades its amplitudes whose local bits lpos[] spell mine[p] against the partner's amplitudes
+ * whose bits spell theirs[p]; of each such pair of blocks it moves the half whose local bit
+ * split_bit equals split_val[p] (the partner moves the other half). */
+typedef struct iqsb_xplan {
+  int32_t npartners; /* 2^k - 1 */
+  int32_t split_bit;
+  int32_t partner[7];
+  int32_t split_val[7];
+  uint64_t mine[7], theirs[7];
+  uint64_t amps_per_partner; /* amplitudes this rank loads from (and stores to) each partner */
+  uint64_t link_amps;        /* amplitudes crossing the link per direction (algorithmic) */
+} iqsb_xplan;
+int iqsb_plan_exchange(int rank, int nranks, unsigned M, int k, const unsigned *lpos, const unsigned *gpos, iqsb_xplan *out);
+/* Placement planning, a pure host function (no GPU needed).  The host library keeps, next to the
+ * reference's qubit_permutation (qubit -> position), a physical placement place[position] = bit of the
+ * distributed index that currently holds it (bits >= M are rank bits).  Given the upcoming gates in
+ * program order (positions; `diagonal` != 0 for diagonal matrices) this picks up to 3 positions to
+ * bring in from rank bits and the local positions to evict for them -- the arguments of ONE
+ * iqsb_exchange_bits call -- by Belady's rule on the next non-diagonal-target use.  Positions in
+ * protect_mask must end up local (they are brought in first) and are never evicted.  last_use (may be
+ * NULL) breaks ties towards the least recently used position; only positions held by local bits
+ * >= min_evict_bit are evicted (low bits would give short runs on the link).
+ * Automates what the reference leaves to the user: PermuteQubits / EmulateSwap
+ * (src/qureg_permute.cpp:10-52, examples/communication_reduction_via_qubit_reordering.cpp:87-132). */
+typedef struct iqsb_pgate {
+  int32_t kind; /* 0: 1-qubit gate on target, 1: controlled gate */
+  int32_t control;
+  int32_t target;
+  int32_t diagonal;
+} iqsb_pgate;
+int iqsb_plan_placement(const uint8_t *place, unsigned n, unsigned M, const iqsb_pgate *gates, int ngates, uint64_t protect_mask,
+                        const uint64_t *last_use, unsigned min_evict_bit, unsigned *evict_pos, unsigned *bring_pos, int *k);
 /* take part in a global-qubit step without owning pairs (ranks whose global control bit is 0,
  * src/qureg_applyctrl1qubitgate.cpp:359-380): same two rendezvous as the gate itself. */
 int iqsb_idle_global(iqsb_state *st);

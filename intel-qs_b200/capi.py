@@ -42,6 +42,21 @@ def plan_global(kind, rank, nranks, M, pos1, pos2):
     return pl
 
 
+class XPlan(ctypes.Structure):
+    _fields_ = [("npartners", ctypes.c_int32), ("split_bit", ctypes.c_int32), ("partner", ctypes.c_int32 * 7), ("split_val", ctypes.c_int32 * 7),
+                ("mine", ctypes.c_uint64 * 7), ("theirs", ctypes.c_uint64 * 7), ("amps_per_partner", ctypes.c_uint64), ("link_amps", ctypes.c_uint64)]
+
+
+def plan_exchange(rank, nranks, M, lpos, gpos):
+    """Host-only: what `rank` moves when local positions lpos are exchanged with global positions gpos."""
+    k = len(lpos)
+    a = (ctypes.c_uint * k)(*lpos)
+    b = (ctypes.c_uint * k)(*gpos)
+    pl = XPlan()
+    _chk(load().iqsb_plan_exchange(rank, nranks, M, k, a, b, ctypes.byref(pl)))
+    return pl
+
+
 def _fgates(gates):
     arr = (FGate * len(gates))()
     for i, (kind, c, t, m) in enumerate(gates):
@@ -154,6 +169,8 @@ def load():
         "iqsb_cgate1_global": [c_vp, c_uint, c_uint, c_uint, c_vp],
         "iqsb_swap2x2_global": [c_vp, c_uint, c_uint, c_uint, c_vp],
         "iqsb_permute_global": [c_vp, c_int, c_int],
+        "iqsb_exchange_bits": [c_vp, c_uint, c_int, c_vp, c_vp],
+        "iqsb_plan_exchange": [c_int, c_int, c_uint, c_int, c_vp, c_vp, c_vp],
     }
     for name, args in sig.items():
         getattr(L, name).argtypes = args
@@ -445,6 +462,10 @@ class State:
     def swap2x2_global(self, M, pos1, pos2, m):
         mm = _m(m)
         _chk(self.L.iqsb_swap2x2_global(self.h, M, pos1, pos2, mm.ctypes.data_as(c_vp)))
+
+    def exchange_bits(self, M, lpos, gpos):
+        k = len(lpos)
+        _chk(self.L.iqsb_exchange_bits(self.h, M, k, (ctypes.c_uint * k)(*lpos), (ctypes.c_uint * k)(*gpos)))
 
     def permute_global(self, src_rank, dst_rank):
         _chk(self.L.iqsb_permute_global(self.h, src_rank, dst_rank))

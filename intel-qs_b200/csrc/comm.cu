@@ -243,7 +243,9 @@ int iqsb_comm_finalize(iqsb_ctx *ctx) {
   return IQSB_OK;
 }
 
-static int peer_barrier(iqsb_ctx *ctx) {
+int iqsb_peer_barrier(iqsb_ctx *ctx);  // also used by exchange.cu
+static int peer_barrier(iqsb_ctx *ctx) { return iqsb_peer_barrier(ctx); }
+int iqsb_peer_barrier(iqsb_ctx *ctx) {
   iqsb_peer_table *pt = ctx->peers;
   pt->epoch++;
   k_barrier<<<1, 32, 0, ctx->stream>>>(pt->d_flags_peer, pt->flags_local, ctx->rank, ctx->nranks, pt->epoch);

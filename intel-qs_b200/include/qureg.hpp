@@ -243,12 +243,19 @@ class QubitRegister {
   void SyncToHost();
   // device handle of the shard (C ABI, include/iqsb.h)
   iqsb_state *DeviceState() { return dev_; }
-  // make the device copy current: flush pending fused gates and write back host-side edits
+  // make the device copy current and in the reference's amplitude order: run queued gates, undo
+  // the placement layer's qubit moves, write back host-side edits
   void PrepareDevice() const {
     const_cast<QubitRegister *>(this)->FlushForRead();
+    RestoreCanonicalPlacement();
     BeforeDeviceOp();
   }
   iqsb_state *DeviceState() const { return dev_; }
+  // placement-layer statistics: multi-bit exchanges run so far and qubits moved by them
+  void GetPlacementStatistics(std::size_t &exchanges, std::size_t &moved_qubits) const {
+    exchanges = exchanges_;
+    moved_qubits = exchanged_bits_;
+  }
 
   // Members (public in the reference)
   std::size_t num_qubits;
@@ -263,7 +270,8 @@ class QubitRegister {
   bool specialize2 = false;
   BaseType overall_sign_of_channels = 1;
 
-  // fusion window
+  // fusion window (the reference's queue type, include/qureg.hpp:398; kept for source compatibility:
+  // this engine queues gates, already resolved to positions, in the private `queue_` below)
   bool fusion;
   unsigned log2llc;
   std::vector<std::tuple<std::string, TM2x2<Type>, unsigned, unsigned>> fwindow;
@@ -289,11 +297,48 @@ class QubitRegister {
   mutable std::vector<std::size_t> checked_out_;  // chunks downloaded since the last device op
   mutable std::vector<unsigned char> chunk_present_;
 
+  // ---- gate queue and placement layer (src/placement.cpp) ----------------------------------
+  // Gates wait in `queue_` (positions, program order) while fusion is on, and -- when the register
+  // spans several GPUs -- for a short look-ahead window also while it is off: the scheduler uses
+  // the gates it can see to decide which qubits to hold in the rank bits.  `place_[position]` is the
+  // PHYSICAL bit of the distributed index that currently holds a position (identity = the
+  // reference's layout: bits >= LocalQubits() are rank bits).  Gates are issued on physical bits;
+  // anything that exposes the raw amplitude order first restores the identity placement.
+  struct QueuedGate {
+    int kind;  // 0: 1-qubit gate, 1: controlled gate
+    unsigned control, target;  // positions
+    bool diagonal;
+    double m[8];
+  };
+  mutable std::vector<QueuedGate> queue_;
+  mutable std::vector<uint8_t> place_, where_;  // position -> physical bit, physical bit -> position
+  mutable std::vector<uint64_t> last_use_;
+  mutable uint64_t use_clock_ = 0;
+  bool placement_ = false;   // several ranks and IQS_B200_PLACEMENT != 0
+  unsigned lookahead_ = 0;   // unfused gates deferred for placement decisions (0: execute at once)
+  mutable uint64_t exchanges_ = 0, exchanged_bits_ = 0;
+
+  void InitPlacement();
+  unsigned Phys(unsigned position) const { return place_.empty() ? position : place_[position]; }
+  bool CanonicalPlacement() const;
+  bool Deferring() const { return fusion || (lookahead_ > 0 && timer == nullptr); }
+  void Enqueue(int kind, unsigned control_position, unsigned target_position, TM2x2<Type> const &m);
+  void RunQueue(std::size_t count);
+  void ExecFusedRange(std::size_t first, std::size_t last);
+  void ExecGate1(unsigned position, const double mm[8], bool diagonal, std::size_t sind, std::size_t eind, const std::string &name);
+  bool ExecCGate1(unsigned control_position, unsigned target_position, const double mm[8], bool diagonal, std::size_t sind,
+                  std::size_t eind, const std::string &name, TM2x2<Type> const *m);
+  void BringLocal(std::size_t queue_from, uint64_t protect_mask);
+  void SwapPlacement(unsigned position_a, unsigned position_b);
+  void RestoreCanonicalPlacement() const;
+  void AlignPlacement(QubitRegister &other);
+  std::size_t PhysicalIndex(std::size_t data_index) const;
+
   void AllocateDevice();
   void ReleaseDevice();
   Type *HostAmplitude(std::size_t index) const;
   void BeforeDeviceOp() const;  // write back host-side edits, prefetch managed pages
-  void FlushForRead();          // flush pending fused gates (strict improvement)
+  void FlushForRead();          // run every queued gate (strict improvement)
   unsigned LocalQubits() const;
   void TimedStart(const std::string &name, std::size_t c, std::size_t t);
   void TimedStop(double algorithmic_bytes, int kind);

@@ -57,6 +57,25 @@ def plan_exchange(rank, nranks, M, lpos, gpos):
     return pl
 
 
+class PGate(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("control", ctypes.c_int32), ("target", ctypes.c_int32), ("diagonal", ctypes.c_int32)]
+
+
+def plan_placement(place, M, gates, protect_mask=0, last_use=None, min_evict_bit=0):
+    """Host-only: (evict positions, bring positions) of the next qubit exchange.  gates = [(kind, control, target, diagonal)]
+    in program order, place[position] = physical bit."""
+    n = len(place)
+    pl = np.ascontiguousarray(place, dtype=np.uint8)
+    arr = (PGate * max(1, len(gates)))()
+    for i, (kind, c, t, d) in enumerate(gates):
+        arr[i].kind, arr[i].control, arr[i].target, arr[i].diagonal = kind, c, t, int(bool(d))
+    lu = None if last_use is None else np.ascontiguousarray(last_use, dtype=np.uint64)
+    ev, br, k = (ctypes.c_uint * 3)(), (ctypes.c_uint * 3)(), c_int()
+    _chk(load().iqsb_plan_placement(pl.ctypes.data_as(c_vp), n, M, arr, len(gates), ctypes.c_uint64(protect_mask),
+                                    None if lu is None else lu.ctypes.data_as(c_vp), min_evict_bit, ev, br, ctypes.byref(k)))
+    return [int(ev[i]) for i in range(k.value)], [int(br[i]) for i in range(k.value)]
+
+
 def _fgates(gates):
     arr = (FGate * len(gates))()
     for i, (kind, c, t, m) in enumerate(gates):
@@ -171,6 +190,7 @@ def load():
         "iqsb_permute_global": [c_vp, c_int, c_int],
         "iqsb_exchange_bits": [c_vp, c_uint, c_int, c_vp, c_vp],
         "iqsb_plan_exchange": [c_int, c_int, c_uint, c_int, c_vp, c_vp, c_vp],
+        "iqsb_plan_placement": [c_vp, c_uint, c_uint, c_vp, c_int, c_u64, c_vp, c_uint, c_vp, c_vp, ctypes.POINTER(c_int)],
     }
     for name, args in sig.items():
         getattr(L, name).argtypes = args

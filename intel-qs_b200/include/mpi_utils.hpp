@@ -11,6 +11,22 @@ enum ReduceOp { SUM = 0, MAX = 1 };
 void AllreduceDouble(double *inout, int n, ReduceOp op);
 // broadcast n doubles from state rank `root`
 void BcastDouble(double *inout, int n, int root);
+
+// Registry of the live registers of this process (B200 engine).  The barriers of this namespace are
+// the program's explicit synchronisation points: they run every register's pending gates and put
+// its amplitudes back in the reference's order, so that after StateBarrier() a rank may read its
+// shard on its own.  Environment::Finalize() releases the device memory of registers still alive.
+namespace detail {
+struct LiveRegister {
+  void *self;
+  void (*settle)(void *self);   // run queued gates + restore the reference's amplitude order (collective)
+  void (*release)(void *self);  // free device memory (the context is going away)
+};
+void RegisterLive(const LiveRegister &r);
+void UnregisterLive(void *self);
+void SettleAllLive();
+void ReleaseAllLive();
+}  // namespace detail
 }  // namespace mpi
 }  // namespace iqs
 #endif

@@ -314,13 +314,14 @@ class QubitRegister {
   mutable std::vector<uint8_t> place_, where_;  // position -> physical bit, physical bit -> position
   mutable std::vector<uint64_t> last_use_;
   mutable uint64_t use_clock_ = 0;
+  mutable bool moved_ = false;  // some position may sit on a physical bit other than its own
   bool placement_ = false;   // several ranks and IQS_B200_PLACEMENT != 0
   unsigned lookahead_ = 0;   // unfused gates deferred for placement decisions (0: execute at once)
   mutable uint64_t exchanges_ = 0, exchanged_bits_ = 0;
 
   void InitPlacement();
   unsigned Phys(unsigned position) const { return place_.empty() ? position : place_[position]; }
-  bool CanonicalPlacement() const;
+  bool CanonicalPlacement() const { return !moved_; }
   bool Deferring() const { return fusion || (lookahead_ > 0 && timer == nullptr); }
   void Enqueue(int kind, unsigned control_position, unsigned target_position, TM2x2<Type> const &m);
   void RunQueue(std::size_t count);

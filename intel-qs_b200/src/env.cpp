@@ -10,6 +10,7 @@
 #include <iostream>
 #include <string>
 #include <thread>
+#include <vector>
 
 #include "../include/bitops.hpp"
 #include "../include/conversion.hpp"
@@ -84,6 +85,43 @@ void create_context(int rank, int nranks, const void *uid, int device) {
 }
 }  // namespace
 
+namespace detail {
+namespace {
+std::vector<LiveRegister> &Live() {
+  static std::vector<LiveRegister> v;
+  return v;
+}
+bool g_settling = false;
+}  // namespace
+void RegisterLive(const LiveRegister &r) { Live().push_back(r); }
+void UnregisterLive(void *self) {
+  auto &v = Live();
+  for (std::size_t i = 0; i < v.size(); ++i)
+    if (v[i].self == self) {
+      v.erase(v.begin() + (std::ptrdiff_t)i);
+      return;
+    }
+}
+// creation order is the same on every rank (SPMD), so the collective steps pair up
+void SettleAllLive() {
+  if (g_settling) return;  // a register's own settle step may pass a barrier
+  g_settling = true;
+  try {
+    std::vector<LiveRegister> snapshot = Live();
+    for (auto &r : snapshot) r.settle(r.self);
+  } catch (...) {
+    g_settling = false;
+    throw;
+  }
+  g_settling = false;
+}
+void ReleaseAllLive() {
+  std::vector<LiveRegister> snapshot = Live();
+  Live().clear();
+  for (auto &r : snapshot) r.release(r.self);
+}
+}  // namespace detail
+
 void Environment::Bootstrap() {
   if (g_ctx) return;
   const char *r = env_first("IQS_RANK", "RANK"), *s = env_first("IQS_NRANKS", "WORLD_SIZE");
@@ -140,6 +178,7 @@ iqsb_ctx *Environment::Context() {
 
 void Environment::InitWithUniqueId(int rank, int nranks, const void *uid128, int device) {
   if (g_ctx) return;
+  g_finalized = false;
   create_context(rank, nranks, uid128, device);
 }
 void Environment::GetUniqueId(void *out128) {
@@ -161,18 +200,22 @@ Environment::~Environment() {
   if (shared_instance == this) {
     shared_instance = nullptr;
     if (g_ctx) {
+      detail::ReleaseAllLive();  // registers that outlive the environment keep no handle into the freed context
       iqsb_finalize(g_ctx);
       g_ctx = nullptr;
+      g_finalized = true;
     }
   }
 }
 
 void Environment::Init() {
   if (shared_instance != nullptr) throw std::runtime_error("iqs::mpi::Environment::Init: environment already initialized");
+  g_finalized = false;
   shared_instance = new Environment();
 }
 void Environment::Init(int &argc, char **&argv) {
   if (shared_instance != nullptr) throw std::runtime_error("iqs::mpi::Environment::Init: environment already initialized");
+  g_finalized = false;
   shared_instance = new Environment(argc, argv);
 }
 void Environment::Finalize() {
@@ -181,11 +224,12 @@ void Environment::Finalize() {
     shared_instance = nullptr;
   }
   if (g_ctx) {
+    detail::ReleaseAllLive();
     iqsb_finalize(g_ctx);
     g_ctx = nullptr;
-    g_finalized = false;  // a later Init() may start a new context
     g_num_states = 1;
   }
+  g_finalized = true;  // Context() no longer bootstraps silently; Init() starts a new environment
 }
 
 // Pool of states (reference src/mpi_env.cpp:279-360): the useful ranks are split into num_states
@@ -229,13 +273,19 @@ Type Environment::IncoherentSumOverAllStatesOfPool(Type local_value) {
 template float Environment::IncoherentSumOverAllStatesOfPool<float>(float);
 template double Environment::IncoherentSumOverAllStatesOfPool<double>(double);
 
-// Barriers also drain the engine's stream: after StateBarrier() the host may read managed state.
+// Barriers are the program's synchronisation points: they run every live register's queued gates,
+// put its amplitudes back in the reference's order (a collective step when qubits were moved between
+// local and rank bits) and drain the engine's stream -- after StateBarrier() a rank may read its shard.
 void PoolBarrier() {
+  if (g_ctx) detail::SettleAllLive();
   if (g_ctx && iqsb_barrier(g_ctx) != IQSB_OK) die("barrier failed");
 }
 void StateBarrier() {
   if (Environment::GetStateSize() > 1) PoolBarrier();
-  else if (g_ctx && iqsb_sync(g_ctx) != IQSB_OK) die("synchronisation failed");
+  else {
+    if (g_ctx) detail::SettleAllLive();
+    if (g_ctx && iqsb_sync(g_ctx) != IQSB_OK) die("synchronisation failed");
+  }
 }
 void Barrier() { PoolBarrier(); }
 

@@ -61,10 +61,20 @@ void QubitRegister<Type>::AllocateDevice() {
   host_touched_ = false;
   checked_out_.clear();
   chunk_present_.clear();
+  iqs::mpi::detail::LiveRegister live;
+  live.self = this;
+  live.settle = [](void *self) {
+    QubitRegister<Type> *r = static_cast<QubitRegister<Type> *>(self);
+    r->FlushForRead();
+    r->RestoreCanonicalPlacement();
+  };
+  live.release = [](void *self) { static_cast<QubitRegister<Type> *>(self)->ReleaseDevice(); };
+  iqs::mpi::detail::RegisterLive(live);
 }
 
 template <class Type>
 void QubitRegister<Type>::ReleaseDevice() {
+  iqs::mpi::detail::UnregisterLive(this);
   if (dev_) {
     iqsb_free(dev_);
     dev_ = nullptr;
@@ -79,6 +89,11 @@ void QubitRegister<Type>::ReleaseDevice() {
 template <class Type>
 Type *QubitRegister<Type>::HostAmplitude(std::size_t index) const {
   assert(index < LocalSize() + TmpSize());
+  if (!queue_.empty() || !CanonicalPlacement()) {
+    // the host sees the state after every gate issued so far, in the reference's amplitude order
+    const_cast<QubitRegister<Type> *>(this)->FlushForRead();
+    RestoreCanonicalPlacement();
+  }
   if (managed_) {
     if (!host_touched_) {
       Check(iqsb_sync(iqs::mpi::Environment::Context()), "synchronising before a host access");
@@ -129,6 +144,7 @@ void QubitRegister<Type>::BeforeDeviceOp() const {
 template <class Type>
 Type *QubitRegister<Type>::RawState() {
   FlushForRead();
+  RestoreCanonicalPlacement();
   if (managed_) {
     Check(iqsb_sync(iqs::mpi::Environment::Context()), "synchronising before a host access");
     host_touched_ = true;
@@ -143,6 +159,7 @@ Type *QubitRegister<Type>::RawState() {
 template <class Type>
 void QubitRegister<Type>::SyncToHost() {
   FlushForRead();
+  RestoreCanonicalPlacement();
   Check(iqsb_sync(iqs::mpi::Environment::Context()), "synchronising");
   if (!managed_ && mirror_) {
     BeforeDeviceOp();
@@ -152,7 +169,7 @@ void QubitRegister<Type>::SyncToHost() {
 
 template <class Type>
 void QubitRegister<Type>::FlushForRead() {
-  if (fusion && !fwindow.empty()) ApplyFusedGates();
+  if (!queue_.empty()) RunQueue(queue_.size());
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -180,6 +197,10 @@ template <class Type>
 void QubitRegister<Type>::Resize(std::size_t new_num_amplitudes) {
   unsigned log2_nprocs = iqs::ilog2(iqs::mpi::Environment::GetStateSize());
   if (GlobalSize()) assert(GlobalSize() * 2UL == new_num_amplitudes);
+  if (dev_) {
+    FlushForRead();
+    RestoreCanonicalPlacement();
+  }
   iqsb_state *old = dev_;
   bool old_managed = managed_;
   std::size_t old_local = local_size_;
@@ -207,6 +228,7 @@ void QubitRegister<Type>::Resize(std::size_t new_num_amplitudes) {
   }
   if (qubit_permutation) delete qubit_permutation;
   qubit_permutation = new Permutation(num_qubits);
+  InitPlacement();
 }
 
 template <class Type>
@@ -237,6 +259,7 @@ void QubitRegister<Type>::Initialize(std::size_t new_num_qubits, std::size_t tmp
   if (this->tmp_spacesize_ > (UL(1) << 26)) this->tmp_spacesize_ = UL(1) << 26;
   this->num_qubits = new_num_qubits;
   qubit_permutation = new Permutation(new_num_qubits);
+  InitPlacement();
   if (do_print_extra_info && !iqs::mpi::Environment::GetStateRank()) printf("Specialization is off\n");
   timer = nullptr;
   gate_counter = nullptr;
@@ -290,7 +313,9 @@ QubitRegister<Type>::QubitRegister(std::size_t new_num_qubits, std::string style
 template <class Type>
 void QubitRegister<Type>::Initialize(std::string style, std::size_t base_index) {
   BeforeDeviceOp();
-  fwindow.clear();
+  queue_.clear();  // the state is overwritten: pending gates and qubit moves are moot
+  for (std::size_t p = 0; p < place_.size(); ++p) place_[p] = where_[p] = (uint8_t)p;
+  moved_ = false;
   Check(iqsb_fill_const(dev_, 0., 0.), "clearing the state");
   if (style == "rand") {
     // Same stream layout as the reference (qureg_init.cpp:256-332): numbers are drawn on the host
@@ -330,6 +355,9 @@ QubitRegister<Type>::QubitRegister(const QubitRegister &in) {
   in.BeforeDeviceOp();
   Check(iqsb_copy(dev_, in.dev_), "copying a register");
   *qubit_permutation = *(in.qubit_permutation);
+  place_ = in.place_;  // the shard is copied as it lies, with the source's placement
+  where_ = in.where_;
+  moved_ = in.moved_;
 }
 
 template <class Type>
@@ -337,6 +365,7 @@ QubitRegister<Type>::~QubitRegister() {
   try {
     if (imported_state && dev_ && mirror_) {
       FlushForRead();
+      RestoreCanonicalPlacement();
       BeforeDeviceOp();
       iqsb_download(dev_, mirror_, 0, LocalSize());
     }
@@ -378,6 +407,7 @@ bool QubitRegister<Type>::operator==(const QubitRegister &rhs) {
   assert(rhs.qubit_permutation->map == qubit_permutation->map);
   FlushForRead();
   const_cast<QubitRegister &>(rhs).FlushForRead();
+  AlignPlacement(const_cast<QubitRegister &>(rhs));
   BeforeDeviceOp();
   rhs.BeforeDeviceOp();
   int eq = 0;
@@ -391,6 +421,7 @@ typename QubitRegister<Type>::BaseType QubitRegister<Type>::MaxAbsDiff(QubitRegi
   assert(x.qubit_permutation->map == qubit_permutation->map);
   FlushForRead();
   x.FlushForRead();
+  AlignPlacement(x);
   BeforeDeviceOp();
   x.BeforeDeviceOp();
   double s[2] = {sfactor.real(), sfactor.imag()}, v = 0;
@@ -405,6 +436,7 @@ typename QubitRegister<Type>::BaseType QubitRegister<Type>::MaxL2NormDiff(QubitR
   assert(x.qubit_permutation->map == qubit_permutation->map);
   FlushForRead();
   x.FlushForRead();
+  AlignPlacement(x);
   BeforeDeviceOp();
   x.BeforeDeviceOp();
   double v = 0;
@@ -418,7 +450,7 @@ Type QubitRegister<Type>::GetGlobalAmplitude(std::size_t global_index) const {
   assert(global_index < global_size_);
   const_cast<QubitRegister *>(this)->FlushForRead();
   BeforeDeviceOp();
-  global_index = qubit_permutation->program2data_(global_index);
+  global_index = PhysicalIndex(qubit_permutation->program2data_(global_index));
   std::size_t hosting_rank = global_index / local_size_, local_index = global_index % local_size_;
   double v[2] = {0, 0};
   if ((int)hosting_rank == iqs::mpi::Environment::GetStateRank()) Check(iqsb_get_amp(dev_, local_index, &v[0], &v[1]), "GetGlobalAmplitude");
@@ -431,7 +463,7 @@ void QubitRegister<Type>::SetGlobalAmplitude(std::size_t global_index, Type valu
   assert(global_index < global_size_);
   FlushForRead();
   BeforeDeviceOp();
-  global_index = qubit_permutation->program2data_(global_index);
+  global_index = PhysicalIndex(qubit_permutation->program2data_(global_index));
   std::size_t hosting_rank = global_index / local_size_, local_index = global_index % local_size_;
   if ((int)hosting_rank == iqs::mpi::Environment::GetStateRank())
     Check(iqsb_set_amp(dev_, local_index, value.real(), value.imag()), "SetGlobalAmplitude");
@@ -447,7 +479,7 @@ void QubitRegister<Type>::Normalize() {
 template <class Type>
 void QubitRegister<Type>::InitializationWithSameAmplitudeEverywhere(Type amplitude) {
   BeforeDeviceOp();
-  fwindow.clear();
+  queue_.clear();  // every amplitude is overwritten (and the constant state has no qubit order)
   Check(iqsb_fill_const(dev_, amplitude.real(), amplitude.imag()), "InitializationWithSameAmplitudeEverywhere");
 }
 
@@ -466,6 +498,7 @@ void QubitRegister<Type>::AmplitudeWiseSum(QubitRegister<Type> &psi, Type factor
   assert(LocalSize() == psi.LocalSize());
   FlushForRead();
   psi.FlushForRead();
+  AlignPlacement(psi);
   BeforeDeviceOp();
   psi.BeforeDeviceOp();
   double f[2] = {factor.real(), factor.imag()};
@@ -488,6 +521,7 @@ Type QubitRegister<Type>::ComputeOverlap(QubitRegister<Type> &psi) {
   assert(psi.qubit_permutation->map == qubit_permutation->map);
   FlushForRead();
   psi.FlushForRead();
+  AlignPlacement(psi);
   BeforeDeviceOp();
   psi.BeforeDeviceOp();
   double v[2] = {0, 0};

@@ -16,8 +16,10 @@
 //     TurnOnSpecialize() (1q.cpp:213-219, ctrl.cpp:363-368, 383-391); here it is unconditional.
 //   * gates on global qubits run as one peer-memory kernel per rank (csrc/comm.cu), not as
 //     Sendrecv / Loop_SN / Sendrecv phases.
-//   * fusion queues every gate with a local target (tiles are built from arbitrary positions); the
-//     flush rules are the reference's, plus a flush before every read of the state.
+//   * fusion queues every gate (tiles are built from arbitrary positions); the flush rules are the
+//     reference's, plus a flush before every read of the state.
+//   * with several ranks a qubit held by a rank bit is swapped in ONCE when a non-diagonal gate
+//     needs it and then stays local (the placement layer, src/placement.cpp).
 #include "qureg_impl.hpp"
 
 namespace iqs {
@@ -67,23 +69,15 @@ double QubitRegister<Type>::HP_DistrSwap(unsigned low_position, unsigned high_po
 // =============================================================================================
 // 1-qubit gates
 // =============================================================================================
+// One 1-qubit gate NOW on the physical bit that holds `position`, over the index range [sind, eind).
 template <class Type>
-bool QubitRegister<Type>::Apply1QubitGate_helper(unsigned qubit_, TM2x2<Type> const &m, std::size_t sind, std::size_t eind,
-                                                 GateSpec1Q spec, BaseType angle) {
-  assert(qubit_ < num_qubits);
-  unsigned position = (*qubit_permutation)[qubit_];
-  assert(position < num_qubits);
-  unsigned myrank = iqs::mpi::Environment::GetStateRank();
-  unsigned M = LocalQubits();
-  std::size_t P = position;
-  std::size_t src_glb_start = UL(myrank) * LocalSize();
-  bool diagonal = IsDiagonal(m);
-  double mm[8];
-  M8(m, mm);
-  BeforeDeviceOp();
+void QubitRegister<Type>::ExecGate1(unsigned position, const double mm[8], bool diagonal, std::size_t sind, std::size_t eind,
+                                    const std::string &name) {
+  const unsigned myrank = iqs::mpi::Environment::GetStateRank();
+  const unsigned M = LocalQubits();
+  const std::size_t P = Phys(position);
   std::string gate_name;
-  if (timer) gate_name = "SQG(" + iqs::toString(P) + ")::" + m.name;
-
+  if (timer) gate_name = "SQG(" + iqs::toString(P) + ")::" + name;
   if (P < M) {
     assert(eind - sind <= LocalSize());
     TimedStart(gate_name, P, 999999);
@@ -96,35 +90,49 @@ bool QubitRegister<Type>::Apply1QubitGate_helper(unsigned qubit_, TM2x2<Type> co
       Check(iqsb_gate1(dev_, (unsigned)P, mm, sind, eind), "1-qubit gate");
       TimedStop(2.0 * sizeof(Type) * double(eind - sind), 1);
     }
-  } else {
-    assert(eind - sind == LocalSize());
-    if (diagonal) {
-      TimedStart(gate_name, P, 999999);
-      const double *s = check_bit(src_glb_start, P) == 0 ? &mm[0] : &mm[6];
-      Check(iqsb_scale(dev_, s, sind, eind), "diagonal gate on a global qubit");
-      // every rank takes part in the global-qubit step so that streams stay in lock step
-      TimedStop(2.0 * sizeof(Type) * double(eind - sind), 0);
-    } else {
-      TimedStart(gate_name, P, 999999);
-      HP_Distrpair((unsigned)P, m, spec, angle);
-      TimedStop(double(LocalSize()) * sizeof(Type), 3);
-    }
+    return;
   }
+  assert(eind - sind == LocalSize());
+  TimedStart(gate_name, P, 999999);
+  if (diagonal) {
+    // a diagonal gate on a rank bit is a per-rank constant: no communication
+    const double *s = ((myrank >> (P - M)) & 1) == 0 ? &mm[0] : &mm[6];
+    Check(iqsb_scale(dev_, s, sind, eind), "diagonal gate on a global qubit");
+    TimedStop(2.0 * sizeof(Type) * double(eind - sind), 0);
+  } else {
+    // only reached with the placement layer off: one peer-memory pair kernel per rank
+    Check(iqsb_gate1_global(dev_, M, (unsigned)P, mm), "gate on a global qubit");
+    TimedStop(double(LocalSize()) * sizeof(Type), 3);
+  }
+}
+
+template <class Type>
+bool QubitRegister<Type>::Apply1QubitGate_helper(unsigned qubit_, TM2x2<Type> const &m, std::size_t sind, std::size_t eind,
+                                                 GateSpec1Q, BaseType) {
+  assert(qubit_ < num_qubits);
+  unsigned position = (*qubit_permutation)[qubit_];
+  assert(position < num_qubits);
+  FlushForRead();  // "now" means after everything queued before it
+  const bool full = (sind == 0 && eind == LocalSize());
+  if (!full) RestoreCanonicalPlacement();  // sub-ranges are ranges of the reference's amplitude order
+  bool diagonal = IsDiagonal(m);
+  double mm[8];
+  M8(m, mm);
+  BeforeDeviceOp();
+  if (placement_ && !diagonal && Phys(position) >= LocalQubits()) BringLocal(queue_.size(), uint64_t(1) << position);
+  ExecGate1(position, mm, diagonal, sind, eind, m.name);
   return true;
 }
 
 template <class Type>
 void QubitRegister<Type>::Apply1QubitGate(unsigned qubit, TM2x2<Type> const &m, GateSpec1Q spec, BaseType angle) {
   if (gate_counter != nullptr) gate_counter->OneQubitIncrement(qubit);
+  assert(qubit < num_qubits);
   unsigned position = (*qubit_permutation)[qubit];
   assert(position < num_qubits);
-  if (fusion == true) {
-    if (position < log2llc) {
-      if (fwindow.size() >= 4000) ApplyFusedGates();  // bound the window
-      fwindow.push_back(std::make_tuple(std::string("sqg"), m, qubit, 0U));
-      return;
-    }
-    ApplyFusedGates();
+  if (Deferring()) {
+    Enqueue(0, 0U, position, m);
+    return;
   }
   Apply1QubitGate_helper(qubit, m, 0UL, LocalSize(), spec, angle);
 }
@@ -236,31 +244,22 @@ void QubitRegister<Type>::ApplyT(unsigned const qubit) {
 // =============================================================================================
 // controlled 1-qubit gates
 // =============================================================================================
+// One controlled gate NOW; C and T below are PHYSICAL bits.  The 4-way (control, target) x (local,
+// rank bit) split is the reference's (ctrl.cpp:290-411).
 template <class Type>
-bool QubitRegister<Type>::ApplyControlled1QubitGate_helper(unsigned control_qubit, unsigned target_qubit, TM2x2<Type> const &m,
-                                                          std::size_t sind, std::size_t eind, GateSpec2Q spec, BaseType angle) {
-  assert(control_qubit != target_qubit);
-  assert(control_qubit < num_qubits);
-  assert(target_qubit < num_qubits);
-  unsigned control_position = (*qubit_permutation)[control_qubit];
-  unsigned target_position = (*qubit_permutation)[target_qubit];
-  assert(control_position < num_qubits);
-  assert(target_position < num_qubits);
-  std::size_t C = control_position, T = target_position;
-  unsigned myrank = iqs::mpi::Environment::GetStateRank();
-  unsigned M = LocalQubits();
+bool QubitRegister<Type>::ExecCGate1(unsigned control_position, unsigned target_position, const double mm[8], bool diagonal,
+                                     std::size_t sind, std::size_t eind, const std::string &name, TM2x2<Type> const *) {
+  const std::size_t C = Phys(control_position), T = Phys(target_position);
+  const unsigned myrank = iqs::mpi::Environment::GetStateRank();
+  const unsigned M = LocalQubits();
   bool HasDoneWork = false;
-  std::size_t src_glb_start = UL(myrank) * LocalSize();
-  bool diagonal = IsDiagonal(m);
-  double mm[8];
-  M8(m, mm);
-  BeforeDeviceOp();
   std::string gate_name;
-  if (timer) gate_name = "CSQG(" + iqs::toString(C) + "," + iqs::toString(T) + ")::" + m.name;
+  if (timer) gate_name = "CSQG(" + iqs::toString(C) + "," + iqs::toString(T) + ")::" + name;
   TimedStart(gate_name, C, T);
   double bytes = 0;
   int kind = 2;
   bool full = (sind == 0 && eind == LocalSize());
+  auto rank_bit = [&](std::size_t physical) { return (myrank >> (physical - M)) & 1u; };
 
   if (C < M && T < M) {
     if (C > T && LocalSize() > (eind - sind) && (eind - sind) <= (UL(1) << C)) {
@@ -283,27 +282,26 @@ bool QubitRegister<Type>::ApplyControlled1QubitGate_helper(unsigned control_qubi
       HasDoneWork = true;
     }
   } else if (C >= M && T < M) {
-    assert(C > T);
-    if (((myrank >> (C - M)) % 2) != 0) {
+    if (rank_bit(C)) {
       Check(iqsb_gate1(dev_, (unsigned)T, mm, sind, eind), "controlled gate (global control)");
       bytes = 2.0 * sizeof(Type) * double(eind - sind);
       kind = 1;
       HasDoneWork = true;
     }
   } else if (C >= M && T >= M) {
-    bool active = ((myrank >> (C - M)) % 2) != 0;
+    bool active = rank_bit(C) != 0;
     if (diagonal) {
       if (active) {
-        const double *s = check_bit(src_glb_start, T) == 0 ? &mm[0] : &mm[6];
+        const double *s = rank_bit(T) == 0 ? &mm[0] : &mm[6];
         Check(iqsb_scale(dev_, s, sind, eind), "controlled diagonal gate (global qubits)");
         bytes = 2.0 * sizeof(Type) * double(eind - sind);
         kind = 0;
         HasDoneWork = true;
       }
     } else {
-      // only the ranks whose control bit is set own pairs; the others keep the barriers company
+      // placement layer off: only the ranks whose control bit is set own pairs; the others keep the barriers company
       if (active) {
-        HP_Distrpair((unsigned)T, m, ConvertSpec2to1(spec), angle);
+        Check(iqsb_gate1_global(dev_, M, (unsigned)T, mm), "gate on a global qubit");
         bytes = double(LocalSize()) * sizeof(Type);
         HasDoneWork = true;
       } else {
@@ -311,41 +309,56 @@ bool QubitRegister<Type>::ApplyControlled1QubitGate_helper(unsigned control_qubi
       }
       kind = 3;
     }
-  } else if (C < M && T >= M) {
+  } else {  // C < M && T >= M
     if (diagonal) {
       // amplitudes with control = 1 are multiplied by m00 or m11 according to this rank's target bit
-      const double *s = check_bit(src_glb_start, T) == 0 ? &mm[0] : &mm[6];
+      const double *s = rank_bit(T) == 0 ? &mm[0] : &mm[6];
       const double one[2] = {1., 0.};
       Check(iqsb_phase_by_bit(dev_, -1, (unsigned)C, one, s), "controlled diagonal gate (global target)");
       bytes = 1.0 * sizeof(Type) * double(eind - sind);
       kind = 1;
     } else {
-      HP_Distrpair((unsigned)C, (unsigned)T, m, spec, angle);
+      Check(iqsb_cgate1_global(dev_, M, (unsigned)C, (unsigned)T, mm), "controlled gate on a global target");
       bytes = 0.5 * double(LocalSize()) * sizeof(Type);
       kind = 3;
     }
     HasDoneWork = true;
-  } else {
-    assert(0);
   }
   TimedStop(bytes, kind);
   return HasDoneWork;
 }
 
 template <class Type>
+bool QubitRegister<Type>::ApplyControlled1QubitGate_helper(unsigned control_qubit, unsigned target_qubit, TM2x2<Type> const &m,
+                                                          std::size_t sind, std::size_t eind, GateSpec2Q, BaseType) {
+  assert(control_qubit != target_qubit);
+  assert(control_qubit < num_qubits);
+  assert(target_qubit < num_qubits);
+  unsigned control_position = (*qubit_permutation)[control_qubit];
+  unsigned target_position = (*qubit_permutation)[target_qubit];
+  assert(control_position < num_qubits);
+  assert(target_position < num_qubits);
+  FlushForRead();
+  const bool full = (sind == 0 && eind == LocalSize());
+  if (!full) RestoreCanonicalPlacement();
+  bool diagonal = IsDiagonal(m);
+  double mm[8];
+  M8(m, mm);
+  BeforeDeviceOp();
+  if (placement_ && !diagonal && Phys(target_position) >= LocalQubits()) BringLocal(queue_.size(), uint64_t(1) << target_position);
+  return ExecCGate1(control_position, target_position, mm, diagonal, sind, eind, m.name, &m);
+}
+
+template <class Type>
 void QubitRegister<Type>::ApplyControlled1QubitGate(unsigned control_qubit, unsigned target_qubit, TM2x2<Type> const &m,
                                                     GateSpec2Q spec, BaseType angle) {
   assert(target_qubit < num_qubits);
+  assert(control_qubit < num_qubits);
+  assert(control_qubit != target_qubit);
   if (gate_counter != nullptr) gate_counter->TwoQubitIncrement(control_qubit, target_qubit);
-  if (fusion == true) {
-    unsigned target_position = (*qubit_permutation)[target_qubit];
-    assert(target_position < num_qubits);
-    if (target_position < log2llc) {
-      if (fwindow.size() >= 4000) ApplyFusedGates();  // bound the window
-      fwindow.push_back(std::make_tuple(std::string("cqg"), m, control_qubit, target_qubit));
-      return;
-    }
-    ApplyFusedGates();
+  if (Deferring()) {
+    Enqueue(1, (*qubit_permutation)[control_qubit], (*qubit_permutation)[target_qubit], m);
+    return;
   }
   ApplyControlled1QubitGate_helper(control_qubit, target_qubit, m, 0UL, LocalSize(), spec, angle);
 }
@@ -473,7 +486,7 @@ void QubitRegister<Type>::Apply4thRootISwap(unsigned qubit1, unsigned qubit2) {
 template <class Type>
 bool QubitRegister<Type>::ApplySwap_helper(unsigned qubit_1, unsigned qubit_2, TM2x2<Type> const &m) {
   if (gate_counter != nullptr) gate_counter->TwoQubitIncrement(qubit_1, qubit_2);
-  if (fusion == true) ApplyFusedGates();
+  FlushForRead();
   assert(qubit_1 < num_qubits);
   assert(qubit_2 < num_qubits);
   assert(qubit_1 != qubit_2);
@@ -491,15 +504,33 @@ bool QubitRegister<Type>::ApplySwap_helper(unsigned qubit_1, unsigned qubit_2, T
   double mm[8];
   M8(m, mm);
   BeforeDeviceOp();
+  const bool is_x = mm[0] == 0. && mm[1] == 0. && mm[2] == 1. && mm[3] == 0. && mm[4] == 1. && mm[5] == 0. && mm[6] == 0. && mm[7] == 0.;
+  if (placement_ && (Phys(position_1) >= M || Phys(position_2) >= M)) {
+    if (is_x) {
+      // SWAP with a qubit held by a rank bit: the two positions trade their physical bits -- no data
+      // moves now; whoever needs the raw amplitude order later pays for the restore
+      SwapPlacement(position_1, position_2);
+      return true;
+    }
+    BringLocal(queue_.size(), (uint64_t(1) << position_1) | (uint64_t(1) << position_2));
+  }
+  unsigned P1 = Phys(position_1), P2 = Phys(position_2);
   std::string gate_name;
-  if (timer) gate_name = "TQG(" + iqs::toString(position_1) + "," + iqs::toString(position_2) + ")::" + m.name;
-  TimedStart(gate_name, position_1, position_2);
-  if (position_1 < M && position_2 < M) {
-    Check(iqsb_swap2x2(dev_, position_1, position_2, mm), "swap-like gate");
+  if (timer) gate_name = "TQG(" + iqs::toString(P1) + "," + iqs::toString(P2) + ")::" + m.name;
+  TimedStart(gate_name, P1, P2);
+  if (P1 > P2) {
+    // the 2x2 acts on {position_1 = 1, position_2 = 0} <-> {position_1 = 0, position_2 = 1}; with the
+    // physical bits in the other order the two basis states trade places: m -> X m X
+    std::swap(P1, P2);
+    std::swap(mm[0], mm[6]); std::swap(mm[1], mm[7]);
+    std::swap(mm[2], mm[4]); std::swap(mm[3], mm[5]);
+  }
+  if (P1 < M && P2 < M) {
+    Check(iqsb_swap2x2(dev_, P1, P2, mm), "swap-like gate");
     TimedStop(1.0 * sizeof(Type) * double(LocalSize()), 2);
   } else {
-    HP_DistrSwap(position_1, position_2, m);
-    TimedStop((position_1 < M ? 0.5 : 1.0) * sizeof(Type) * double(LocalSize()), 3);
+    Check(iqsb_swap2x2_global(dev_, M, P1, P2, mm), "swap-like gate on a global qubit");
+    TimedStop((P1 < M ? 0.5 : 1.0) * sizeof(Type) * double(LocalSize()), 3);
   }
   return true;
 }
@@ -512,13 +543,20 @@ void QubitRegister<Type>::ApplyDiag(unsigned qubit_1, unsigned qubit_2, TM4x4<Ty
   assert(qubit_1 < num_qubits);
   assert(qubit_2 < num_qubits);
   if (gate_counter != nullptr) gate_counter->TwoQubitIncrement(qubit_1, qubit_2);
-  if (fusion == true) ApplyFusedGates();
+  ApplyDiagSimp(qubit_1, qubit_2, m);
+}
+
+template <class Type>
+void QubitRegister<Type>::ApplyDiagSimp(unsigned qubit_1, unsigned qubit_2, TM4x4<Type> const &m) {
+  // same result as ApplyDiag without the statistics bookkeeping (applydiag.cpp:17-51)
+  FlushForRead();
   unsigned position_1 = (*qubit_permutation)[qubit_1];
   unsigned position_2 = (*qubit_permutation)[qubit_2];
   assert(position_1 < num_qubits);
   assert(position_2 < num_qubits);
   // index of the diagonal entry = 2*bit(position_1) + bit(position_2)  (applydiag.cpp:157-224);
-  // 64-bit shifts: the reference's `1 << position` overflows for positions >= 31
+  // 64-bit shifts: the reference's `1 << position` overflows for positions >= 31.
+  // A diagonal gate never communicates: bits held by rank bits are read from this rank's number.
   double d[8];
   for (int k = 0; k < 4; ++k) {
     d[2 * k] = m[k][k].real();
@@ -526,23 +564,7 @@ void QubitRegister<Type>::ApplyDiag(unsigned qubit_1, unsigned qubit_2, TM4x4<Ty
   }
   BeforeDeviceOp();
   std::size_t glb_start = UL(iqs::mpi::Environment::GetStateRank()) * LocalSize();
-  Check(iqsb_diag2(dev_, position_1, position_2, d, glb_start), "ApplyDiag");
-}
-
-template <class Type>
-void QubitRegister<Type>::ApplyDiagSimp(unsigned qubit_1, unsigned qubit_2, TM4x4<Type> const &m) {
-  // same result as ApplyDiag without the statistics / fusion bookkeeping (applydiag.cpp:17-51)
-  if (fusion == true) ApplyFusedGates();
-  unsigned position_1 = (*qubit_permutation)[qubit_1];
-  unsigned position_2 = (*qubit_permutation)[qubit_2];
-  double d[8];
-  for (int k = 0; k < 4; ++k) {
-    d[2 * k] = m[k][k].real();
-    d[2 * k + 1] = m[k][k].imag();
-  }
-  BeforeDeviceOp();
-  std::size_t glb_start = UL(iqs::mpi::Environment::GetStateRank()) * LocalSize();
-  Check(iqsb_diag2(dev_, position_1, position_2, d, glb_start), "ApplyDiagSimp");
+  Check(iqsb_diag2(dev_, Phys(position_1), Phys(position_2), d, glb_start), "ApplyDiag");
 }
 
 // Declared but never defined in the reference (qureg.hpp:255-256); provided as aliases of ApplyDiag.
@@ -554,11 +576,11 @@ void QubitRegister<Type>::ApplyDiagGeneral(unsigned qubit_1, unsigned qubit_2, T
 template <class Type>
 void QubitRegister<Type>::Apply2QubitGate(unsigned const qubit_high, unsigned const qubit_low, TM4x4<Type> const &m) {
   // the basis index is 2*bit(high) + bit(low).  The reference is single-rank only (2q.cpp:23:
-  // assert on the state size).  Here a global position is first exchanged with a free local one
-  // (exact data movement over NVLink: the SWAP path with m = X), the 4x4 is applied locally and the
-  // exchange is undone -- so the gathered state equals the single-rank result bit for bit.
+  // assert on the state size).  Here a qubit held by a rank bit is first made local by the placement
+  // layer (exact data movement over NVLink) and stays local afterwards; with the layer switched off
+  // it is swapped in and out again around the gate.
   assert(qubit_low < num_qubits && qubit_high < num_qubits && qubit_low != qubit_high);
-  if (fusion == true) ApplyFusedGates();
+  FlushForRead();
   unsigned position_high = (*qubit_permutation)[qubit_high];
   unsigned position_low = (*qubit_permutation)[qubit_low];
   double mm[32];
@@ -569,28 +591,34 @@ void QubitRegister<Type>::Apply2QubitGate(unsigned const qubit_high, unsigned co
     }
   BeforeDeviceOp();
   const unsigned M = LocalQubits();
-  const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
-  unsigned pos[2] = {position_high, position_low};
-  unsigned moved_from[2], moved_to[2];
-  int nmoved = 0;
-  if (position_high >= M || position_low >= M) {
-    if (M < 2) throw std::invalid_argument("Apply2QubitGate on global qubits needs at least two local qubits");
-    unsigned candidate = M;  // highest free local position first
-    for (int k = 0; k < 2; ++k) {
-      if (pos[k] < M) continue;
-      do {
-        --candidate;
-      } while (candidate == pos[0] || candidate == pos[1]);
-      Check(iqsb_swap2x2_global(dev_, M, candidate, pos[k], X), "Apply2QubitGate: bringing a global qubit to a local position");
-      moved_from[nmoved] = pos[k];
-      moved_to[nmoved] = candidate;
-      ++nmoved;
-      pos[k] = candidate;
+  if (placement_) {
+    if (M < 3) throw std::invalid_argument("Apply2QubitGate on global qubits needs at least three local qubits");
+    BringLocal(queue_.size(), (uint64_t(1) << position_high) | (uint64_t(1) << position_low));
+    Check(iqsb_gate2(dev_, Phys(position_high), Phys(position_low), mm), "Apply2QubitGate");
+  } else {
+    const double X[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+    unsigned pos[2] = {position_high, position_low};
+    unsigned moved_from[2], moved_to[2];
+    int nmoved = 0;
+    if (position_high >= M || position_low >= M) {
+      if (M < 2) throw std::invalid_argument("Apply2QubitGate on global qubits needs at least two local qubits");
+      unsigned candidate = M;  // highest free local position first
+      for (int k = 0; k < 2; ++k) {
+        if (pos[k] < M) continue;
+        do {
+          --candidate;
+        } while (candidate == pos[0] || candidate == pos[1]);
+        Check(iqsb_swap2x2_global(dev_, M, candidate, pos[k], X), "Apply2QubitGate: bringing a global qubit to a local position");
+        moved_from[nmoved] = pos[k];
+        moved_to[nmoved] = candidate;
+        ++nmoved;
+        pos[k] = candidate;
+      }
     }
+    Check(iqsb_gate2(dev_, pos[0], pos[1], mm), "Apply2QubitGate");
+    for (int k = nmoved - 1; k >= 0; --k)
+      Check(iqsb_swap2x2_global(dev_, M, moved_to[k], moved_from[k], X), "Apply2QubitGate: returning a qubit to its global position");
   }
-  Check(iqsb_gate2(dev_, pos[0], pos[1], mm), "Apply2QubitGate");
-  for (int k = nmoved - 1; k >= 0; --k)
-    Check(iqsb_swap2x2_global(dev_, M, moved_to[k], moved_from[k], X), "Apply2QubitGate: returning a qubit to its global position");
   if (gate_counter != nullptr) gate_counter->TwoQubitIncrement(qubit_high, qubit_low);
 }
 
@@ -608,14 +636,13 @@ void QubitRegister<Type>::ApplyToffoli(unsigned const control_1, unsigned const 
   V_dag(0, 1) = {1.0 / 2.0, -1.0 / 2.0};
   V_dag(1, 0) = {1.0 / 2.0, -1.0 / 2.0};
   V_dag(1, 1) = {1.0 / 2.0, 1.0 / 2.0};
-  // With all three qubits local the five gates go through the fusion queue as one batch: the same
-  // arithmetic in the same order, but ONE sweep of the state (a shared-memory tile holding the three
-  // positions) instead of five half-sweeps.
+  // With fusion off the five gates still go through the queue as one batch: the same arithmetic in
+  // the same order, but ONE sweep of the state (a shared-memory tile holding the three positions)
+  // instead of five half-sweeps.
   unsigned M = LocalQubits();
-  bool batch = !fusion && M >= 4 && (*qubit_permutation)[control_1] < M && (*qubit_permutation)[control_2] < M && (*qubit_permutation)[target] < M;
-  unsigned saved_log2llc = log2llc;
+  bool batch = !fusion && M >= 4 && (placement_ || iqs::mpi::Environment::GetStateSize() == 1);
   if (batch) {
-    log2llc = M;
+    FlushForRead();
     fusion = true;
   }
   ApplyControlled1QubitGate(control_1, target, V);
@@ -624,9 +651,8 @@ void QubitRegister<Type>::ApplyToffoli(unsigned const control_1, unsigned const 
   ApplyCPauliX(control_2, control_1);
   ApplyControlled1QubitGate(control_2, target, V);
   if (batch) {
-    ApplyFusedGates();
+    FlushForRead();
     fusion = false;
-    log2llc = saved_log2llc;
   }
 }
 
@@ -643,8 +669,9 @@ void QubitRegister<Type>::TurnOnFusion(unsigned log2llc_) {
   } else {
     // The reference sizes a contiguous block for the CPU's last-level cache (default 2^20 amplitudes)
     // and can only fuse gates whose target lies below log2llc.  The GPU engine builds its shared-memory
-    // tiles from arbitrary positions (csrc/kernels_fused.cu), so EVERY gate with a local target is
-    // queued; `log2llc` only keeps its role of switching fusion on.
+    // tiles from arbitrary positions (csrc/kernels_fused.cu), so EVERY gate is queued; `log2llc` only
+    // keeps its role of switching fusion on.
+    FlushForRead();  // gates deferred for look-ahead so far run unfused, as they were issued
     this->log2llc = M;
     if (!myrank) printf("Fusion is enabled: log2llc = %u (requested %u; every local target is fused) num_qubits = %lu\n", this->log2llc, log2llc_, num_qubits);
     fusion = true;
@@ -653,7 +680,7 @@ void QubitRegister<Type>::TurnOnFusion(unsigned log2llc_) {
 
 template <class Type>
 void QubitRegister<Type>::TurnOffFusion() {
-  if (fwindow.size()) ApplyFusedGates();
+  FlushForRead();
   fusion = false;
 }
 
@@ -664,53 +691,7 @@ bool QubitRegister<Type>::IsFusionEnabled() {
 
 template <class Type>
 void QubitRegister<Type>::ApplyFusedGates() {
-  if (fwindow.empty()) return;
-  if (fwindow.size() == 1) {  // a window of one gate is applied as a plain gate (fusion.cpp:75)
-    auto f = fwindow[0];
-    fwindow.clear();
-    if (std::get<0>(f) == "sqg") Apply1QubitGate_helper(std::get<2>(f), std::get<1>(f), 0UL, LocalSize());
-    else ApplyControlled1QubitGate_helper(std::get<2>(f), std::get<3>(f), std::get<1>(f), 0UL, LocalSize());
-    return;
-  }
-  unsigned myrank = iqs::mpi::Environment::GetStateRank();
-  unsigned M = LocalQubits();
-  std::vector<iqsb_fgate> batch;
-  batch.reserve(fwindow.size());
-  for (auto &f : fwindow) {
-    iqsb_fgate g;
-    std::string &type = std::get<0>(f);
-    M8(std::get<1>(f), g.m);
-    g.pad = 0;
-    if (type == "sqg") {
-      g.kind = 0;
-      g.control = 0;
-      g.target = (int)(*qubit_permutation)[std::get<2>(f)];
-    } else if (type == "cqg") {
-      unsigned C = (*qubit_permutation)[std::get<2>(f)];
-      g.target = (int)(*qubit_permutation)[std::get<3>(f)];
-      if (C >= M) {  // global control: the gate exists only on the ranks whose bit is set
-        if (((myrank >> (C - M)) % 2) == 0) continue;
-        g.kind = 0;
-        g.control = 0;
-      } else {
-        g.kind = 1;
-        g.control = (int)C;
-      }
-    } else {
-      assert(0);
-      continue;
-    }
-    batch.push_back(g);
-  }
-  fwindow.clear();
-  BeforeDeviceOp();
-  TimedStart("FUSED(" + iqs::toString(batch.size()) + ")", 0, 999999);
-  const int kMaxPerCall = 4096;
-  for (std::size_t first = 0; first < batch.size(); first += kMaxPerCall) {
-    int count = (int)std::min<std::size_t>(kMaxPerCall, batch.size() - first);
-    Check(iqsb_fused(dev_, batch.data() + first, count), "fused gate batch");
-  }
-  TimedStop(2.0 * sizeof(Type) * double(LocalSize()), 1);
+  FlushForRead();
 }
 
 template class QubitRegister<ComplexSP>;

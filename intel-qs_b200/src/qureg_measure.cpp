@@ -19,7 +19,7 @@ bool QubitRegister<Type>::IsClassicalBit(unsigned qubit, BaseType tolerance) con
   BeforeDeviceOp();
   std::size_t glb_start = UL(iqs::mpi::Environment::GetStateRank()) * LocalSize();
   int flags[2] = {0, 0};
-  Check(iqsb_any_above(dev_, position, (double)tolerance, glb_start, flags), "IsClassicalBit");
+  Check(iqsb_any_above(dev_, Phys(position), (double)tolerance, glb_start, flags), "IsClassicalBit");
   double v[2] = {double(flags[0]), double(flags[1])};
   iqs::mpi::AllreduceDouble(v, 2, iqs::mpi::MAX);  // logical OR over the ranks (measure.cpp:69-70)
   return !(v[0] > 0 && v[1] > 0);
@@ -33,11 +33,12 @@ void QubitRegister<Type>::CollapseQubit(unsigned qubit, bool value) {
   FlushForRead();
   BeforeDeviceOp();
   unsigned M = LocalQubits();
-  if (position < M) {
-    Check(iqsb_collapse(dev_, position, value ? 1 : 0), "CollapseQubit");
+  const unsigned P = Phys(position);  // the physical bit that holds the position (src/placement.cpp)
+  if (P < M) {
+    Check(iqsb_collapse(dev_, P, value ? 1 : 0), "CollapseQubit");
   } else {
     std::size_t glb_start = UL(iqs::mpi::Environment::GetStateRank()) * LocalSize();
-    if (check_bit(glb_start, position) != value) Check(iqsb_fill_const(dev_, 0., 0.), "CollapseQubit");
+    if (check_bit(glb_start, P) != value) Check(iqsb_fill_const(dev_, 0., 0.), "CollapseQubit");
   }
 }
 
@@ -49,12 +50,13 @@ typename QubitRegister<Type>::BaseType QubitRegister<Type>::GetProbability(unsig
   FlushForRead();
   BeforeDeviceOp();
   unsigned M = LocalQubits();
+  const unsigned P = Phys(position);
   double p = 0.;
-  if (position < M) {
-    Check(iqsb_prob1(dev_, position, &p), "GetProbability");
+  if (P < M) {
+    Check(iqsb_prob1(dev_, P, &p), "GetProbability");
   } else {
     std::size_t glb_start = UL(iqs::mpi::Environment::GetStateRank()) * LocalSize();
-    if (check_bit(glb_start, position) == 1) Check(iqsb_norm2(dev_, &p), "GetProbability");
+    if (check_bit(glb_start, P) == 1) Check(iqsb_norm2(dev_, &p), "GetProbability");
   }
   iqs::mpi::AllreduceDouble(&p, 1, iqs::mpi::SUM);
   return (BaseType)p;
@@ -69,7 +71,7 @@ bool QubitRegister<Type>::GetClassicalValue(unsigned qubit, BaseType tolerance) 
   BeforeDeviceOp();
   std::size_t glb_start = UL(iqs::mpi::Environment::GetStateRank()) * LocalSize();
   int flags[2] = {0, 0};
-  Check(iqsb_any_above(dev_, position, (double)tolerance, glb_start, flags), "GetClassicalValue");
+  Check(iqsb_any_above(dev_, Phys(position), (double)tolerance, glb_start, flags), "GetClassicalValue");
   double v[2] = {double(flags[0]), double(flags[1])};
   iqs::mpi::AllreduceDouble(v, 2, iqs::mpi::MAX);
   bool zero = v[0] > 0, one = v[1] > 0;
@@ -148,8 +150,8 @@ typename QubitRegister<Type>::BaseType QubitRegister<Type>::ExpectationValue(std
   std::size_t myrank = iqs::mpi::Environment::GetStateRank();
   std::size_t glb_start = UL(myrank) * LocalSize();
   std::size_t y = 0;
-  for (std::size_t i = 0; i < qubits.size(); i++) y += std::size_t(1) << (*qubit_permutation)[qubits[i]];
-  FlushForRead();
+  FlushForRead();  // may move qubits between local and rank bits: build the mask afterwards
+  for (std::size_t i = 0; i < qubits.size(); i++) y += std::size_t(1) << Phys((*qubit_permutation)[qubits[i]]);
   BeforeDeviceOp();
   double v = 0;
   Check(iqsb_parity_expect(dev_, y, glb_start, &v), "ExpectationValue");

@@ -23,6 +23,7 @@ std::vector<Type> Snapshot(iqsb_state *dev, std::size_t n) {
 template <class Type>
 void QubitRegister<Type>::Print(std::string x, std::vector<std::size_t>) {
   FlushForRead();
+  RestoreCanonicalPlacement();
   BeforeDeviceOp();
   int my_rank = iqs::mpi::Environment::GetStateRank(), nprocs = iqs::mpi::Environment::GetStateSize();
   std::vector<Type> host = Snapshot<Type>(dev_, LocalSize());
@@ -52,6 +53,7 @@ void QubitRegister<Type>::Print(std::string x, std::vector<std::size_t>) {
 template <class Type>
 void QubitRegister<Type>::ExportAmplitudes(std::string ofname) {
   FlushForRead();
+  RestoreCanonicalPlacement();
   BeforeDeviceOp();
   int my_rank = iqs::mpi::Environment::GetStateRank(), nprocs = iqs::mpi::Environment::GetStateSize();
   std::vector<Type> host = Snapshot<Type>(dev_, LocalSize());
@@ -80,6 +82,7 @@ template <class Type>
 void QubitRegister<Type>::dumpbin(std::string fn) {
   // raw amplitudes, rank r at byte offset r * LocalSize() * sizeof(Type) (the reference's MPI-IO layout)
   FlushForRead();
+  RestoreCanonicalPlacement();
   BeforeDeviceOp();
   int my_rank = iqs::mpi::Environment::GetStateRank(), nprocs = iqs::mpi::Environment::GetStateSize();
   std::vector<Type> host = Snapshot<Type>(dev_, LocalSize());

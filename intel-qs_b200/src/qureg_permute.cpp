@@ -53,6 +53,7 @@ void QubitRegister<Type>::PermuteLocalQubits(std::vector<std::size_t> new_map, s
   if (old_inverse_map == new_inverse_map) return;
 
   FlushForRead();
+  RestoreCanonicalPlacement();
   BeforeDeviceOp();
   // amplitude i (old data index) moves to program2data_new(data2program_old(i)): bit `pos` of i
   // belongs to qubit old_imap[pos] and lands on position new_map[that qubit]
@@ -89,6 +90,7 @@ void QubitRegister<Type>::PermuteGlobalQubits(std::vector<std::size_t> new_map, 
     }
   }
   FlushForRead();
+  RestoreCanonicalPlacement();
   BeforeDeviceOp();
   Check(iqsb_permute_global(dev_, (int)source, (int)destination), "PermuteGlobalQubits");
   qubit_permutation->SetNewPermutationFromMap(new_map, style_of_map);

@@ -199,13 +199,16 @@ def run_driver(driver, program, state=None, init=1, base_index=0, threads=None, 
         r = subprocess.run(cmd, env=env, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"driver failed ({r.returncode}): {r.stdout[-2000:]}\n{r.stderr[-2000:]}")
-        secs = None
+        secs = settled = None
         for line in r.stdout.splitlines():
             if line.startswith("TIME "):
-                secs = float(line.split()[1])
+                f = line.split()
+                secs = float(f[1])
+                if "SETTLED" in f:
+                    settled = float(f[f.index("SETTLED") + 1])
         if env.get("IQS_DRIVER_TRACE"):
             print(r.stderr)
-        out = {"seconds": secs, "stdout": r.stdout}
+        out = {"seconds": secs, "seconds_settled": settled, "stdout": r.stdout}
         out["scalars"] = np.fromfile(os.path.join(td, "scal.bin"), dtype=np.float64) if os.path.exists(os.path.join(td, "scal.bin")) else np.zeros(0)
         out["map"] = np.fromfile(os.path.join(td, "map.bin"), dtype=np.uint64).astype(np.int64)
         out["state"] = np.fromfile(os.path.join(td, "out.bin"), dtype=np.complex128) if want_state else None

@@ -35,16 +35,27 @@ def run_ranks(oracle, nranks, prog, state=None, **kw):
     return oracle.run_driver(DRIVER, prog, state=state, launcher=launcher, **kw)
 
 
+def random_unitary_for(rng):
+    from progs import random_unitary
+
+    return random_unitary(rng)
+
+
 def need(n):
     if NGPU < n:
         pytest.skip(f"needs {n} GPUs, {NGPU} visible")
 
 
 @pytest.mark.parametrize("nranks", [2, 4, 8])
-def test_gates_and_permutations_sharded_bit_exact(oracle, nranks):
+@pytest.mark.parametrize("mode", ["placement", "eager", "pairkernels"])
+def test_gates_and_permutations_sharded_bit_exact(oracle, nranks, mode):
     """Every gate kind on local and global qubits, interleaved with local / global / mixed qubit
-    permutations (qureg_permute_test.hpp): the gathered state equals the oracle bit for bit."""
+    permutations (qureg_permute_test.hpp): the gathered state equals the oracle bit for bit.
+    mode: the placement layer with its look-ahead queue (default), without look-ahead, or switched
+    off (gates on rank bits run as peer-memory pair kernels, the reference's HP_Distrpair replaced
+    one to one)."""
     need(nranks)
+    env = {"placement": {}, "eager": {"IQS_B200_LOOKAHEAD": "0"}, "pairkernels": {"IQS_B200_PLACEMENT": "0"}}[mode]
     n, seed = 12, 2
     rng = np.random.default_rng(nranks)
     prog = random_program(n, 200, seed, toffoli=True)
@@ -56,7 +67,7 @@ def test_gates_and_permutations_sharded_bit_exact(oracle, nranks):
     prog.extend(random_program(n, 40, seed + 2))
     psi = C.random_state(n, seed)
     want, _, wmap = oracle.run_program(n, psi, prog.ops)
-    got = run_ranks(oracle, nranks, prog, state=psi)
+    got = run_ranks(oracle, nranks, prog, state=psi, extra_env=env)
     assert np.array_equal(got["map"], wmap)
     err = np.max(np.abs(got["state"] - want))
     assert err <= TOL, f"{nranks} ranks: max |amp - oracle| = {err}"
@@ -91,8 +102,8 @@ def test_qft_sharded(oracle, nranks):
     assert np.max(np.abs(got["state"] - want)) <= TOL
 
 
-@pytest.mark.parametrize("nranks", [2])
-def test_fusion_sharded(oracle, nranks):
+@pytest.mark.parametrize("nranks,placement", [(2, "1"), (2, "0"), (8, "1")])
+def test_fusion_sharded(oracle, nranks, placement):
     need(nranks)
     n = 13
     prog = C.Program(n).mode(C.FUSION_ON, 8)
@@ -100,8 +111,37 @@ def test_fusion_sharded(oracle, nranks):
     prog.mode(C.FUSION_OFF)
     psi = C.random_state(n, 6)
     want, _, _ = oracle.run_program(n, psi, prog.ops)
-    got = run_ranks(oracle, nranks, prog, state=psi)
+    got = run_ranks(oracle, nranks, prog, state=psi, extra_env={"IQS_B200_PLACEMENT": placement})
     assert np.array_equal(got["state"], want)
+
+
+@pytest.mark.parametrize("nranks", [2, 4, 8])
+def test_placement_layer_reads_between_moves(oracle, nranks):
+    """Qubits travel between local bits and rank bits while the program keeps reading: probabilities,
+    expectation values, single amplitudes, collapse, SWAPs with global qubits (relabelled, no data
+    moved), a permutation in the middle (forces the reference's layout back) -- scalars to 1e-12,
+    final gathered state bit for bit."""
+    need(nranks)
+    n, seed = 12, 21
+    rng = np.random.Generator(np.random.MT19937(seed))
+    prog = C.Program(n)
+    for rnd in range(6):
+        for q in range(n - 1, -1, -1):
+            prog.gate1(q, random_unitary_for(rng))
+        prog.named2(C.SWAP, 0, n - 1).named2(C.SWAP, n - 2, n - 1).named2(C.ISWAP, 1, n - 1).named2(C.SQRTISWAP, n - 1, n - 3)
+        prog.named2(C.CX, n - 1, 2).named2(C.CX, 2, n - 1).named2(C.CPHASE, n - 1, n - 2, 0.3).named1(C.T, n - 1)
+        prog.prob(n - 1).prob(0).expect([n - 1, 0], [1, 2]).expect1(n - 2, 2).get_amp(int(rng.integers(0, 1 << n))).get_amp((1 << n) - 1)
+        if rnd == 2:
+            prog.permute([int(x) for x in rng.permutation(n)])
+        if rnd == 4:
+            prog.named1(C.H, n - 1).collapse(n - 1, 1).normalize().emuswap(3, n - 1)
+        prog.toffoli(n - 1, 4, n - 2)
+    psi = C.random_state(n, seed)
+    want, wsc, wmap = oracle.run_program(n, psi, prog.ops)
+    got = run_ranks(oracle, nranks, prog, state=psi)
+    assert np.array_equal(got["map"], wmap)
+    assert got["scalars"].size == wsc.size and np.max(np.abs(got["scalars"] - wsc)) <= TOL
+    assert np.array_equal(got["state"], want), np.max(np.abs(got["state"] - want))
 
 
 @pytest.mark.parametrize("nranks", [2, 4])

@@ -69,6 +69,12 @@ def main():
     timeit("swap_global(local M-1, glob)", lambda: st.swap2x2_global(M, M - 1, M + k - 1, X), 8.0 * L)
     if k >= 2:
         timeit("swap_global(glob, glob)", lambda: st.swap2x2_global(M, M, M + 1, X), 16.0 * L)
+    # the placement layer's primitive: k local positions <-> k global positions in one pass;
+    # each call is undone by the next one (same arguments), so the state is preserved
+    for kk in range(1, min(k, 3) + 1):
+        gl = [M + j for j in range(kk)]
+        for name, lo in (("high", [M - 1 - j for j in range(kk)]), ("mid", [12 + 3 * j for j in range(kk)]), ("low5", [5 + j for j in range(kk)])):
+            timeit(f"exchange_bits(k={kk}, {name} {lo})", lambda lo=lo, gl=gl: st.exchange_bits(M, lo, gl), 16.0 * L * (1.0 - 2.0 ** -kk))
     timeit("permute_global(pair swap)", lambda: st.permute_global(rank ^ 1, rank ^ 1), 16.0 * L)
     timeit("permute_global(shift 1)", lambda: st.permute_global((rank + 1) % world, (rank - 1) % world), 16.0 * L)
     timeit("local gate1(pos 10) [ref]", lambda: st.gate1(10, C.G_FIXED), 32.0 * L)

@@ -150,15 +150,25 @@ typedef struct iqsb_fgate {
   double m[8];
 } iqsb_fgate;
 /* Apply `ngates` gates in order with as few sweeps over HBM as possible.  Targets and controls may
- * be ANY local positions: the batch is cut into runs of consecutive gates whose targets fit in one
+ * be ANY local positions: the batch is cut into runs of gates whose targets fit in one
  * shared-memory tile (2^12 amplitudes = the 4 lowest positions + 8 positions chosen per run); each
- * run costs one read and one write of the state. */
+ * run costs one read and one write of the state.  Inside a run, gates on up to three tile bits are
+ * applied in registers per shared-memory round trip, with arithmetic specialised to the zero
+ * structure of each matrix (values identical to the full evaluation for finite amplitudes). */
 int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates);
 /* tile exponent (12, or log2(local_amps) for tiny shards) */
 int iqsb_fused_max_log2tile(const iqsb_state *st);
 /* Pure host function: the runs iqsb_fused would execute.  run_end[r] = one past the last gate of
  * run r; tiles[16 r] = number of tile positions, tiles[16 r + 1 ..] = the positions (ascending); tiles holds 16 bytes per run. */
 int iqsb_plan_fused(const iqsb_fgate *gates, int ngates, unsigned log2_local, int *run_end, uint8_t *tiles, int max_runs, int *nruns);
+/* Pure host function: the plan iqsb_fused really executes.  Runs are cut in program order, except
+ * that a pure-permutation gate (X / CNOT: matrix entries exactly 0 and 1) may move ahead of gates on
+ * OTHER qubits into an earlier run -- that commutation involves no rounding, so the result is bit
+ * for bit the one of the program order (reorder = 0 switches it off; IQS_B200_FUSED_REORDER=0 does
+ * so for iqsb_fused).  order[k] = index of the k-th gate executed, run_end[r] = one past the last
+ * entry of run r in order[], tiles as for iqsb_plan_fused. */
+int iqsb_plan_fused_order(const iqsb_fgate *gates, int ngates, unsigned log2_local, int reorder, int *order, int *run_end, uint8_t *tiles,
+                          int max_runs, int *nruns);
 
 /* ---- reductions (warp-shuffle + fixed-order second stage; deterministic run to run) -- */
 /* sum |a|^2 over local amplitudes with bit pos == 1: GetProbability (src/qureg_measure.cpp:150-167) */

@@ -102,6 +102,24 @@ def plan_fused(gates, log2_local):
     return out
 
 
+def plan_fused_order(gates, log2_local, reorder=True):
+    """Host-only: the plan iqsb_fused executes -- [(gate indices in execution order, tile positions)] per run.
+    With reorder, exact X / CNOT gates may move ahead of gates on other qubits (bit-exact commutation)."""
+    arr = _fgates(gates)
+    n = len(gates)
+    order = (c_int * max(n, 1))()
+    run_end = (c_int * max(n, 1))()
+    tiles = np.zeros(16 * max(n, 1), dtype=np.uint8)
+    nruns = c_int()
+    _chk(load().iqsb_plan_fused_order(arr, n, log2_local, int(bool(reorder)), order, run_end, tiles.ctypes.data_as(c_vp), max(n, 1), ctypes.byref(nruns)))
+    out, first = [], 0
+    for r in range(nruns.value):
+        ns = int(tiles[16 * r])
+        out.append(([int(order[k]) for k in range(first, int(run_end[r]))], tiles[16 * r + 1 : 16 * r + 1 + ns].astype(int).tolist()))
+        first = int(run_end[r])
+    return out
+
+
 def plan_permute(dst_bit):
     """Host-only: list of (positions, dstslot) tile phases for a local qubit permutation."""
     a = np.ascontiguousarray(dst_bit, dtype=np.uint8)
@@ -164,6 +182,7 @@ def load():
         "iqsb_fused": [c_vp, c_vp, c_int],
         "iqsb_fused_max_log2tile": [c_vp],
         "iqsb_plan_fused": [c_vp, c_int, c_uint, c_vp, c_vp, c_int, ctypes.POINTER(c_int)],
+        "iqsb_plan_fused_order": [c_vp, c_int, c_uint, c_int, c_vp, c_vp, c_vp, c_int, ctypes.POINTER(c_int)],
         "iqsb_prob1": [c_vp, c_uint, ctypes.POINTER(c_dbl)],
         "iqsb_parity_expect": [c_vp, c_u64, c_u64, ctypes.POINTER(c_dbl)],
         "iqsb_norm2": [c_vp, ctypes.POINTER(c_dbl)],

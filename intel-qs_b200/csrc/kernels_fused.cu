@@ -1,25 +1,42 @@
 // kernels_fused.cu -- gate fusion: a batch of gates applied in as few sweeps over HBM as
-// possible, the amplitudes staged in shared-memory tiles.
+// possible, the amplitudes staged in shared-memory tiles and worked on in registers.
 //
 // Replaces ApplyFusedGates (reference src/qureg_fusion.cpp:55-94), which replays the queued gates
 // block by block, with blocks of 2^log2llc CONTIGUOUS amplitudes sized for the CPU's last-level
 // cache -- so only gates whose target lies below log2llc can be fused there.
 //
-// Here a tile is the set of 2^K amplitudes (K = 12: 64 KiB of ComplexDP) whose indices differ only
-// in K chosen bit positions pos[0] < pos[1] < ...: the four lowest positions are always part of it
-// (global accesses are 256-byte runs, moved as 32-byte chunks), the other eight are whatever
-// positions the gates of the run act on.  A run of consecutive gates whose targets fit in one tile
-// costs ONE read and ONE write of the state, wherever the target qubits sit; iqsb_fused cuts a
-// batch into such runs greedily.  Controls may be anywhere: inside the tile they are a bit of the
-// tile-local index, outside they select whole tiles (the reference's rule for controls above the
-// block, src/qureg_applyctrl1qubitgate.cpp:296-309).
+// Three levels:
 //
-// Inside a tile every gate is one shared-memory round trip of the tile (16-byte slots, XOR-swizzled
-// so that the 8 lanes of a quarter-warp hit 8 different bank groups for every target slot).
-// Measured (profiles/r01_ncu_summary.md): a run costs one sweep (78-91 % of the copy peak) plus
-// 1.36 ms per gate per 2^30 amplitudes inside the tile, 3.5x cheaper than a sweep per gate; that
-// in-tile cost is bound by the FP64 issue rate of the exact, non-contracted arithmetic (28
-// instructions per pair), 1.05 ms with IQSB_ARITH_FMA (16 instructions, then shared-memory bound).
+//   run    a tile is the set of 2^K amplitudes (K = 12: 64 KiB of ComplexDP) whose indices differ
+//          only in K chosen bit positions: the four lowest positions are always part of it (global
+//          accesses are 256-byte runs), the other eight are whatever positions the gates of the run
+//          act on.  A run costs ONE read and ONE write of the state, wherever its target qubits
+//          sit.  Controls may be anywhere: outside the tile they select whole tiles (the reference's
+//          rule for controls above the block, src/qureg_applyctrl1qubitgate.cpp:296-309).
+//   group  inside a run, consecutive gates whose targets fall on at most THREE tile bits form a
+//          group: every thread takes the 8 amplitudes spanned by those three bits into registers,
+//          applies all gates of the group there and writes them back -- one shared-memory round
+//          trip and one __syncthreads per group instead of per gate (round 1: per gate, 73 % of the
+//          shared-memory wavefront budget).
+//   gate   each gate is classified on the host by the zero structure of its matrix (general / real
+//          / diagonal / diag(1,d) / anti-diagonal / exact X / real-diagonal+imaginary-off-diagonal
+//          = RX) and the kernel switches once per gate, CTA-uniformly, to code that leaves out the
+//          products with exact zeros and ones: 0-12 instead of 28 FP64 instructions per pair.  For
+//          finite amplitudes the values are identical to the reference's full evaluation (a product
+//          with an exact zero only contributes a signed zero); the reference does the same on the
+//          CPU for named gates (src/spec_kernels.cpp:36-153).
+//
+// Planner (host, exposed as iqsb_plan_fused_order): runs are cut greedily in program order, but a
+// pure-permutation gate (X / CNOT with an exact 0/1 matrix) commutes EXACTLY -- no rounding is
+// involved -- with every gate on other qubits, so it is allowed to move across skipped gates into
+// the earliest run that holds its target.  A layer of 32 one-qubit gates + 16 CNOTs is 4 sweeps
+// instead of 6, bit for bit the same result.  Arithmetic gates never change their relative order.
+//
+// Shared-memory layout: 16-byte slots, slot index i stored at i ^ fold(i) where fold XORs the 3-bit
+// fields i[5:3], i[8:6], i[11:9] into the low three bits.  The 8 lanes of a quarter-warp vary three
+// tile bits chosen by the planner with distinct residues mod 3, which makes every access of a group
+// (and the global<->tile copies) bank-conflict free whatever the group's register bits are.
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -28,57 +45,66 @@
 
 namespace {
 
-// Tuning knobs (compile-time; the defaults are the measured best, profiles/r01_fused_variants.md)
-#ifndef IQSB_FUSED_THREADS
-#define IQSB_FUSED_THREADS 256
-#endif
 #ifndef IQSB_FUSED_MINBLOCKS
-#define IQSB_FUSED_MINBLOCKS 4
+#define IQSB_FUSED_MINBLOCKS 3
 #endif
 #ifndef IQSB_FUSED_TILE
 #define IQSB_FUSED_TILE 12
 #endif
-#ifndef IQSB_FUSED_LOW
-#define IQSB_FUSED_LOW 4
-#endif
-#ifndef IQSB_FUSED_LOADS
-#define IQSB_FUSED_LOADS 2
-#endif
-#ifndef IQSB_FUSED_ASYNC_LOAD
-#define IQSB_FUSED_ASYNC_LOAD 1
-#endif
-#ifndef IQSB_FUSED_PAIR_UNROLL
-#define IQSB_FUSED_PAIR_UNROLL 2
-#endif
-constexpr int kThreads = IQSB_FUSED_THREADS;
+constexpr int kThreads = 256;
 constexpr int kMaxFusedGates = 4096;
 constexpr int kTile = IQSB_FUSED_TILE;  // tile exponent (<= 12)
-constexpr int kLow = IQSB_FUSED_LOW;    // lowest positions always in the tile
-static_assert(kTile >= 9 && kTile <= 11 + 1 && kLow >= 1 && kLow <= 4, "tile geometry");
-constexpr int kPairUnroll = IQSB_FUSED_PAIR_UNROLL;
+constexpr int kLow = 4;                 // lowest positions always in the tile
+constexpr int kRegBits = 3;             // tile bits held in registers by a group
+constexpr int kBatchGates = 48;         // descriptors resident in shared memory at a time
+constexpr int kBatchGroups = 24;
+constexpr int kReorderWindow = 512;     // how far the planner looks past the first skipped gate
+static_assert(kTile >= 9 && kTile <= 12, "tile geometry");
+
+enum GateClass : uint8_t { kGeneral = 0, kReal, kDiag, kDiag1, kAnti, kXExact, kRealDiagImagOff };
 
 template <typename T>
 struct alignas(16) FGate {
   Mat2<T> m;
-  int tslot;  // tile-local bit of the target
-  int ckind;  // 0: none, 1: control is tile-local bit `c`, 2: control is bit `c` of the global index (outside the tile)
-  int c;
-  int pad;
+  uint8_t cls;    // GateClass
+  uint8_t tbit;   // register bit of the target (0..2)
+  uint8_t ckind;  // 0 none | 1 register bit (pairs enabled: `en`) | 2 thread bit `c` | 3 bit `c` of the tile's base index
+  uint8_t c;
+  uint8_t en;     // 4-bit mask of the register pairs the gate acts on
+  uint8_t pad8[3];
+  uint32_t pad32[2];
 };
+
+struct alignas(16) GroupDesc {
+  uint16_t lo[32];  // swizzled slot contributed by thread bits 0..4
+  uint16_t hi[16];  // ... by thread bits 5..8
+  uint16_t p[3];    // swizzled slot offset of register bit k
+  uint16_t gate_first, gate_count;
+  uint16_t log2_threads;  // tile exponent - 3
+  uint16_t pad[2];
+};
+static_assert(sizeof(GroupDesc) == 112, "group descriptor layout");
+
+struct BatchHdr {
+  int ngroups, ngates, pad0, pad1;
+};
+
+template <typename T>
+__host__ __device__ constexpr size_t batch_stride() {
+  return sizeof(BatchHdr) + kBatchGroups * sizeof(GroupDesc) + kBatchGates * sizeof(FGate<T>);
+}
 
 struct TileDesc {
   uint8_t pos[kTile];
   int nS;
 };
 
-// 16-byte slots; swizzle so that pairs (i, i + 2^s) are conflict free for every s
-__device__ __forceinline__ unsigned phys(unsigned i) { return i ^ (((i >> 3) & 1u) * 7u); }
+// 16-byte slots, XOR-folded swizzle (linear over GF(2): swz(a ^ b) == swz(a) ^ swz(b))
+__host__ __device__ __forceinline__ unsigned swz(unsigned i) { return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7u); }
 
 // global -> tile without register staging: one asynchronous 16-byte (ComplexDP) / 8-byte (ComplexSP)
-// copy per amplitude, straight into its swizzled slot (LDGSTS).  Every thread has its whole share
-// of the tile in flight at once, which is what brings the sweep of a run to the copy bandwidth
-// (profiles/r01_ncu_summary.md: 8 x 32 B per thread in one batch = 101 % of the copy peak, but 64
-// staging registers cost a CTA per SM; the asynchronous copies need none).
+// copy per amplitude, straight into its swizzled slot (LDGSTS); every thread has its whole share of
+// the tile in flight at once.
 __device__ __forceinline__ void cp_async_amp(Cx<double> *smem, const Cx<double> *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -88,166 +114,380 @@ __device__ __forceinline__ void cp_async_amp(Cx<float> *smem, const Cx<float> *g
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
 template <typename T>
-__device__ __forceinline__ void tile_load_async(Cx<T> *tile, const Chunk<T> *g, const uint64_t *g_lo, const uint64_t *g_hi, unsigned nchunks) {
+__device__ __forceinline__ void tile_load_async(Cx<T> *tile, const Chunk<T> *g, const uint32_t *g_lo, const uint32_t *g_hi, unsigned nchunks) {
 #pragma unroll 4
   for (unsigned c = threadIdx.x; c < nchunks; c += kThreads) {
-    const Cx<T> *src = reinterpret_cast<const Cx<T> *>(g + (g_lo[c & 255] | g_hi[c >> 8]));
-    cp_async_amp(tile + phys(2 * c), src);
-    cp_async_amp(tile + phys(2 * c + 1), src + 1);
+    const Cx<T> *src = reinterpret_cast<const Cx<T> *>(g + ((uint64_t)g_lo[c & 255] | (uint64_t)g_hi[c >> 8]));
+    const unsigned s = swz(2 * c);
+    cp_async_amp(tile + s, src);
+    cp_async_amp(tile + (s ^ 1u), src + 1);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
-
-// global <-> tile, U 32-byte accesses in flight per thread; nchunks is a multiple of kThreads * U
+// tile -> global, U 32-byte stores in flight per thread; nchunks is a multiple of kThreads * U
 template <typename T, int U>
-__device__ __forceinline__ void tile_load(Cx<T> *tile, const Chunk<T> *g, const uint64_t *g_lo, const uint64_t *g_hi, unsigned nchunks) {
+__device__ __forceinline__ void tile_store(const Cx<T> *tile, Chunk<T> *g, const uint32_t *g_lo, const uint32_t *g_hi, unsigned nchunks) {
 #pragma unroll 1
   for (unsigned c0 = threadIdx.x; c0 < nchunks; c0 += kThreads * U) {
     Chunk<T> v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      unsigned c = c0 + u * kThreads;
-      v[u] = ld_chunk(g + (g_lo[c & 255] | g_hi[c >> 8]));
+      const unsigned s = swz(2 * (c0 + u * kThreads));
+      v[u].a = tile[s];
+      v[u].b = tile[s ^ 1u];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       unsigned c = c0 + u * kThreads;
-      tile[phys(2 * c)] = v[u].a;
-      tile[phys(2 * c + 1)] = v[u].b;
-    }
-  }
-}
-template <typename T, int U>
-__device__ __forceinline__ void tile_store(const Cx<T> *tile, Chunk<T> *g, const uint64_t *g_lo, const uint64_t *g_hi, unsigned nchunks) {
-#pragma unroll 1
-  for (unsigned c0 = threadIdx.x; c0 < nchunks; c0 += kThreads * U) {
-    Chunk<T> v[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      unsigned c = c0 + u * kThreads;
-      v[u].a = tile[phys(2 * c)];
-      v[u].b = tile[phys(2 * c + 1)];
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      unsigned c = c0 + u * kThreads;
-      st_chunk(g + (g_lo[c & 255] | g_hi[c >> 8]), v[u]);
+      st_chunk(g + ((uint64_t)g_lo[c & 255] | (uint64_t)g_hi[c >> 8]), v[u]);
     }
   }
 }
 
-constexpr int kGateBatch = 16;  // gate descriptors staged in shared memory at a time
+// ---- one gate on the 8 register-resident amplitudes -----------------------------------------
+// B = register bit of the target; pair k (k = 0..3) is (a[r0], a[r0 | 1 << B]) with r0 = k with a
+// zero inserted at bit B.  `en` selects the pairs (control on another register bit).
+template <typename T, int B, typename F>
+__device__ __forceinline__ void for_pairs(unsigned en, Cx<T> (&a)[8], F f) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r0 = ((k >> B) << (B + 1)) | (k & ((1 << B) - 1));
+    if (en & (1u << k)) f(a[r0], a[r0 | (1 << B)]);
+  }
+}
+
+template <typename T, bool FMA, int B>
+__device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Mat2<T> &m, Cx<T> (&a)[8]) {
+  switch (cls) {
+    case kXExact:  // out0 = in1, out1 = in0
+      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+        Cx<T> t = x;
+        x = y;
+        y = t;
+      });
+      break;
+    case kDiag1: {  // out0 = in0, out1 = m11 * in1
+      const Cx<T> d = m.m11;
+      for_pairs<T, B>(en, a, [&](Cx<T> &, Cx<T> &y) { y = cmul(d, y); });
+      break;
+    }
+    case kDiag: {
+      const Cx<T> d0 = m.m00, d1 = m.m11;
+      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+        x = cmul(d0, x);
+        y = cmul(d1, y);
+      });
+      break;
+    }
+    case kAnti: {
+      const Cx<T> u = m.m01, l = m.m10;
+      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+        const Cx<T> t = cmul(u, y);
+        y = cmul(l, x);
+        x = t;
+      });
+      break;
+    }
+    case kReal: {  // every imaginary part of the matrix is an exact zero (H, RY)
+      const T r00 = m.m00.re, r01 = m.m01.re, r10 = m.m10.re, r11 = m.m11.re;
+      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+        Cx<T> o0, o1;
+        if (FMA) {
+          o0.re = fma_c(r00, x.re, r01 * y.re);
+          o0.im = fma_c(r00, x.im, r01 * y.im);
+          o1.re = fma_c(r10, x.re, r11 * y.re);
+          o1.im = fma_c(r10, x.im, r11 * y.im);
+        } else {
+          o0.re = add_rn(mul_rn(r00, x.re), mul_rn(r01, y.re));
+          o0.im = add_rn(mul_rn(r00, x.im), mul_rn(r01, y.im));
+          o1.re = add_rn(mul_rn(r10, x.re), mul_rn(r11, y.re));
+          o1.im = add_rn(mul_rn(r10, x.im), mul_rn(r11, y.im));
+        }
+        x = o0;
+        y = o1;
+      });
+      break;
+    }
+    case kRealDiagImagOff: {  // m00, m11 real; m01, m10 imaginary (RX)
+      const T r00 = m.m00.re, i01 = m.m01.im, i10 = m.m10.im, r11 = m.m11.re;
+      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+        Cx<T> o0, o1;
+        if (FMA) {
+          o0.re = fma_c(r00, x.re, -(i01 * y.im));
+          o0.im = fma_c(r00, x.im, i01 * y.re);
+          o1.re = fma_c(r11, y.re, -(i10 * x.im));
+          o1.im = fma_c(r11, y.im, i10 * x.re);
+        } else {
+          o0.re = sub_rn(mul_rn(r00, x.re), mul_rn(i01, y.im));
+          o0.im = add_rn(mul_rn(r00, x.im), mul_rn(i01, y.re));
+          o1.re = add_rn(-mul_rn(i10, x.im), mul_rn(r11, y.re));
+          o1.im = add_rn(mul_rn(i10, x.re), mul_rn(r11, y.im));
+        }
+        x = o0;
+        y = o1;
+      });
+      break;
+    }
+    default:
+      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+        if (FMA) apply2x2_fma(m, x, y);
+        else apply2x2(m, x, y);
+      });
+      break;
+  }
+}
 
 template <typename T, bool FMA>
 __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
-    k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, const FGate<T> *__restrict__ gates, int ngates) {
+    k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, const unsigned char *__restrict__ desc, int nbatches) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cx<T> *tile = reinterpret_cast<Cx<T> *>(smem_raw);
   // chunk offset of tile-local chunk index c = lo | hi << 8 (c = tile-local amplitude index / 2)
-  __shared__ uint64_t g_lo[256], g_hi[8];
-  __shared__ __align__(16) FGate<T> s_gate[kGateBatch];
+  __shared__ uint32_t g_lo[256], g_hi[8];
+  __shared__ __align__(16) GroupDesc s_group[kBatchGroups];
+  __shared__ __align__(16) FGate<T> s_gate[kBatchGates];
   __shared__ int s_pos[16];
+  __shared__ int s_hdr[4];
   const int nS = td.nS;  // pos[0] == 0 always
   if (threadIdx.x < kTile) s_pos[threadIdx.x] = td.pos[threadIdx.x];
   __syncthreads();
   for (unsigned t = threadIdx.x; t < 256 + 8; t += kThreads) {
     unsigned v = t < 256 ? t : (t - 256) << 8;
-    uint64_t go = 0;
+    uint32_t go = 0;
 #pragma unroll 1
     for (int k = 1; k < nS; ++k)
-      if ((v >> (k - 1)) & 1u) go |= 1ull << (s_pos[k] - 1);
+      if ((v >> (k - 1)) & 1u) go |= 1u << (s_pos[k] - 1);
     if (t < 256) g_lo[t] = go;
     else g_hi[t - 256] = go;
   }
+  auto stage = [&](int b) {
+    const unsigned char *src = desc + (size_t)b * batch_stride<T>();
+    const BatchHdr h = *reinterpret_cast<const BatchHdr *>(src);
+    if (threadIdx.x == 0) {
+      s_hdr[0] = h.ngroups;
+      s_hdr[1] = h.ngates;
+    }
+    const int4 *gs = reinterpret_cast<const int4 *>(src + sizeof(BatchHdr));
+    const int ng4 = h.ngroups * (int)(sizeof(GroupDesc) / 16);
+    for (int i = threadIdx.x; i < ng4; i += kThreads) reinterpret_cast<int4 *>(s_group)[i] = __ldg(gs + i);
+    const int4 *fs = reinterpret_cast<const int4 *>(src + sizeof(BatchHdr) + kBatchGroups * sizeof(GroupDesc));
+    const int nf4 = h.ngates * (int)(sizeof(FGate<T>) / 16);
+    for (int i = threadIdx.x; i < nf4; i += kThreads) reinterpret_cast<int4 *>(s_gate)[i] = __ldg(fs + i);
+  };
+  if (nbatches == 1) stage(0);
   __syncthreads();
   const unsigned nchunks = 1u << (nS - 1);
-  constexpr int U = IQSB_FUSED_LOADS;  // 32-byte loads in flight per thread
   for (uint64_t o = blockIdx.x; o < nouter; o += gridDim.x) {
     uint64_t base = o;  // amplitude index with zeros at the tile positions
 #pragma unroll 1
     for (int k = 0; k < nS; ++k) base = insert_zero(base, (unsigned)s_pos[k]);
     Chunk<T> *g = state + (base >> 1);
-#if IQSB_FUSED_ASYNC_LOAD
     tile_load_async<T>(tile, g, g_lo, g_hi, nchunks);
-#else
-    if (nchunks % (kThreads * U) == 0) tile_load<T, U>(tile, g, g_lo, g_hi, nchunks);
-    else tile_load<T, 1>(tile, g, g_lo, g_hi, nchunks);
-#endif
-    for (int g0 = 0; g0 < ngates; g0 += kGateBatch) {
-      // stage the next descriptors (the barrier also orders the tile accesses of the previous gate)
-      const int nb = ngates - g0 < kGateBatch ? ngates - g0 : kGateBatch;
-      constexpr int kWords = (int)(sizeof(FGate<T>) / 16);
-      if (g0) __syncthreads();  // a skipped gate has no barrier of its own: nobody still reads s_gate
-      if ((int)threadIdx.x < nb * kWords)
-        reinterpret_cast<int4 *>(s_gate)[threadIdx.x] = __ldg(reinterpret_cast<const int4 *>(gates + g0) + threadIdx.x);
-      __syncthreads();
-      for (int gi = 0; gi < nb; ++gi) {
-        const unsigned ts = (unsigned)s_gate[gi].tslot;
-        const int ckind = s_gate[gi].ckind;
-        const unsigned cs = (unsigned)s_gate[gi].c;
-        if (ckind == 2 && !((base >> cs) & 1ull)) continue;  // uniform over the CTA
-        const Mat2<T> m = s_gate[gi].m;
-        if (ckind != 1) {
-          const unsigned npairs = 1u << (nS - 1);
-#pragma unroll kPairUnroll
-          for (unsigned j = threadIdx.x; j < npairs; j += kThreads) {
-            const unsigned x = (unsigned)insert_zero(j, ts);
-            const unsigned i0 = phys(x), i1 = phys(x | (1u << ts));
-            Cx<T> a = tile[i0], b = tile[i1];
-            if (FMA) apply2x2_fma(m, a, b);
-            else apply2x2(m, a, b);
-            tile[i0] = a;
-            tile[i1] = b;
+    for (int b = 0; b < nbatches; ++b) {
+      if (nbatches > 1) {
+        if (b) __syncthreads();  // nobody still reads the previous batch
+        stage(b);
+      }
+      __syncthreads();  // the tile is loaded, the descriptors are visible
+      const int ngroups = s_hdr[0];
+      for (int gi = 0; gi < ngroups; ++gi) {
+        const GroupDesc &G = s_group[gi];
+        const unsigned P0 = G.p[0], P1 = G.p[1], P2 = G.p[2];
+        const unsigned nthr = 1u << G.log2_threads;
+        const int gfirst = G.gate_first, glast = gfirst + G.gate_count;
+#pragma unroll 1
+        for (unsigned t = threadIdx.x; t < nthr; t += kThreads) {
+          const unsigned px = (unsigned)G.lo[t & 31u] ^ (unsigned)G.hi[t >> 5];
+          Cx<T> a[8];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) a[r] = tile[px ^ ((r & 1) ? P0 : 0u) ^ ((r & 2) ? P1 : 0u) ^ ((r & 4) ? P2 : 0u)];
+#pragma unroll 1
+          for (int gj = gfirst; gj < glast; ++gj) {
+            const FGate<T> &fg = s_gate[gj];
+            const unsigned cls = fg.cls, tbit = fg.tbit, ckind = fg.ckind, c = fg.c, en = fg.en;
+            if (ckind == 3 && !((base >> c) & 1ull)) continue;  // uniform over the CTA
+            if (ckind == 2 && !((t >> c) & 1u)) continue;       // uniform over the warp when c >= 5 (the planner's choice)
+            if (tbit == 0) apply_on_bit<T, FMA, 0>(cls, en, fg.m, a);
+            else if (tbit == 1) apply_on_bit<T, FMA, 1>(cls, en, fg.m, a);
+            else apply_on_bit<T, FMA, 2>(cls, en, fg.m, a);
           }
-        } else {
-          const unsigned lo = cs < ts ? cs : ts, hi = cs < ts ? ts : cs;
-          const unsigned npairs = 1u << (nS - 2);
-#pragma unroll kPairUnroll
-          for (unsigned j = threadIdx.x; j < npairs; j += kThreads) {
-            const unsigned x = (unsigned)insert_zero(insert_zero(j, lo), hi) | (1u << cs);
-            const unsigned i0 = phys(x), i1 = phys(x | (1u << ts));
-            Cx<T> a = tile[i0], b = tile[i1];
-            if (FMA) apply2x2_fma(m, a, b);
-            else apply2x2(m, a, b);
-            tile[i0] = a;
-            tile[i1] = b;
-          }
+#pragma unroll
+          for (int r = 0; r < 8; ++r) tile[px ^ ((r & 1) ? P0 : 0u) ^ ((r & 2) ? P1 : 0u) ^ ((r & 4) ? P2 : 0u)] = a[r];
         }
         __syncthreads();
       }
     }
-    __syncthreads();  // covers ngates == 0 and a skipped last gate
-    if (nchunks % (kThreads * U) == 0) tile_store<T, U>(tile, g, g_lo, g_hi, nchunks);
+    if (nchunks % (kThreads * 2) == 0) tile_store<T, 2>(tile, g, g_lo, g_hi, nchunks);
     else tile_store<T, 1>(tile, g, g_lo, g_hi, nchunks);
     __syncthreads();
   }
 }
 
-// one run: gates [first, last) of `in` all have their target in the tile `td`
+// ---------------------------------------------------------------------------------------------
+// host: classification, groups, descriptors
+// ---------------------------------------------------------------------------------------------
+bool is_xexact(const double m[8]) {
+  return m[0] == 0. && m[1] == 0. && m[6] == 0. && m[7] == 0. && m[2] == 1. && m[3] == 0. && m[4] == 1. && m[5] == 0.;
+}
+
+uint8_t classify(const double m[8]) {
+  const bool z00 = m[0] == 0. && m[1] == 0., z01 = m[2] == 0. && m[3] == 0., z10 = m[4] == 0. && m[5] == 0., z11 = m[6] == 0. && m[7] == 0.;
+  if (z00 && z11) return is_xexact(m) ? kXExact : kAnti;
+  if (z01 && z10) return (m[0] == 1. && m[1] == 0.) ? kDiag1 : kDiag;
+  if (m[1] == 0. && m[3] == 0. && m[5] == 0. && m[7] == 0.) return kReal;
+  if (m[1] == 0. && m[7] == 0. && m[2] == 0. && m[4] == 0.) return kRealDiagImagOff;
+  return kGeneral;
+}
+
+struct HostGroup {
+  std::vector<int> gates;  // indices into the run's gate list
+  int rs[kRegBits];        // register slots (tile-local bits)
+  int nrs = 0;
+};
+
+// Build the batches (header + groups + gates) of one run.  `run` lists indices into `in`, in
+// execution order; every target is in the tile.
 template <typename T>
-int launch_run(iqsb_state *st, const iqsb_fgate *in, int first, int last, const TileDesc &td) {
-  iqsb_ctx *ctx = st->ctx;
+void build_batches(const iqsb_fgate *in, const std::vector<int> &run, const TileDesc &td, std::vector<unsigned char> &out, int &nbatches) {
+  const int nS = td.nS;
   int slot_of[64];
   for (int p = 0; p < 64; ++p) slot_of[p] = -1;
-  for (int k = 0; k < td.nS; ++k) slot_of[td.pos[k]] = k;
-  std::vector<FGate<T>> gates((size_t)(last - first));
-  for (int k = first; k < last; ++k) {
-    FGate<T> &o = gates[k - first];
-    o.m = make_mat<T>(in[k].m);
-    o.tslot = slot_of[in[k].target];
-    o.pad = 0;
-    o.ckind = 0;
-    o.c = 0;
-    if (in[k].kind == 1) {
-      int c = in[k].control;
-      if (slot_of[c] >= 0) { o.ckind = 1; o.c = slot_of[c]; }
-      else { o.ckind = 2; o.c = c; }
+  for (int k = 0; k < nS; ++k) slot_of[td.pos[k]] = k;
+  // 1. groups: consecutive gates on at most kRegBits distinct target slots
+  std::vector<HostGroup> groups;
+  HostGroup cur;
+  auto close = [&]() {
+    if (!cur.gates.empty()) groups.push_back(cur);
+    cur = HostGroup();
+  };
+  for (size_t k = 0; k < run.size(); ++k) {
+    const int ts = slot_of[in[run[k]].target];
+    bool have = false;
+    for (int j = 0; j < cur.nrs; ++j) have = have || cur.rs[j] == ts;
+    if ((!have && cur.nrs == kRegBits) || (int)cur.gates.size() == kBatchGates) close();
+    have = false;
+    for (int j = 0; j < cur.nrs; ++j) have = have || cur.rs[j] == ts;
+    if (!have) cur.rs[cur.nrs++] = ts;
+    cur.gates.push_back((int)k);
+  }
+  close();
+  // 2. descriptors
+  out.clear();
+  nbatches = 0;
+  BatchHdr hdr = {0, 0, 0, 0};
+  std::vector<GroupDesc> bgroups;
+  std::vector<FGate<T>> bgates;
+  auto flush = [&]() {
+    if (bgroups.empty()) return;
+    hdr.ngroups = (int)bgroups.size();
+    hdr.ngates = (int)bgates.size();
+    size_t off = out.size();
+    out.resize(off + batch_stride<T>(), 0);
+    memcpy(&out[off], &hdr, sizeof(hdr));
+    memcpy(&out[off + sizeof(BatchHdr)], bgroups.data(), bgroups.size() * sizeof(GroupDesc));
+    memcpy(&out[off + sizeof(BatchHdr) + kBatchGroups * sizeof(GroupDesc)], bgates.data(), bgates.size() * sizeof(FGate<T>));
+    bgroups.clear();
+    bgates.clear();
+    ++nbatches;
+  };
+  for (HostGroup &hg : groups) {
+    if ((int)bgroups.size() == kBatchGroups || bgates.size() + hg.gates.size() > (size_t)kBatchGates) flush();
+    bool used[16] = {false};
+    for (int j = 0; j < hg.nrs; ++j) used[hg.rs[j]] = true;
+    // tile-local controls of the group
+    bool is_ctrl[16] = {false};
+    for (int k : hg.gates) {
+      const iqsb_fgate &q = in[run[k]];
+      if (q.kind == 1 && slot_of[q.control] >= 0) is_ctrl[slot_of[q.control]] = true;
+    }
+    // spare register bits: controls first (the gate then acts on whole register pairs), then any slot
+    for (int s = 0; s < nS && hg.nrs < kRegBits; ++s)
+      if (is_ctrl[s] && !used[s]) { hg.rs[hg.nrs++] = s; used[s] = true; }
+    for (int s = nS - 1; s >= 0 && hg.nrs < kRegBits; --s)
+      if (!used[s]) { hg.rs[hg.nrs++] = s; used[s] = true; }
+    // thread bits -> tile slots.  Bits 0..2 (the lanes of a quarter-warp): three slots with distinct
+    // residues mod 3, preferably not controls; controls go to the highest thread bits (warp-uniform).
+    int dep[16], ndep = 0;
+    bool taken[16] = {false};
+    for (int pass = 0; pass < 2; ++pass)
+      for (int res = 0; res < 3; ++res) {
+        bool have = false;
+        for (int j = 0; j < ndep; ++j) have = have || dep[j] % 3 == res;
+        if (have || ndep >= 3) continue;
+        for (int s = 0; s < nS; ++s)
+          if (!used[s] && !taken[s] && s % 3 == res && (pass == 1 || !is_ctrl[s])) { dep[ndep++] = s; taken[s] = true; break; }
+      }
+    for (int s = 0; s < nS; ++s)
+      if (!used[s] && !taken[s] && !is_ctrl[s]) { dep[ndep++] = s; taken[s] = true; }
+    for (int s = 0; s < nS; ++s)
+      if (!used[s] && !taken[s]) { dep[ndep++] = s; taken[s] = true; }
+    int tbit_of[16];
+    for (int s = 0; s < 16; ++s) tbit_of[s] = -1;
+    for (int j = 0; j < ndep; ++j) tbit_of[dep[j]] = j;
+    GroupDesc gd;
+    memset(&gd, 0, sizeof(gd));
+    for (unsigned v = 0; v < 32; ++v) {
+      unsigned x = 0;
+      for (int k = 0; k < 5 && k < ndep; ++k)
+        if ((v >> k) & 1u) x |= 1u << dep[k];
+      gd.lo[v] = (uint16_t)swz(x);
+    }
+    for (unsigned v = 0; v < 16; ++v) {
+      unsigned x = 0;
+      for (int k = 5; k < ndep; ++k)
+        if ((v >> (k - 5)) & 1u) x |= 1u << dep[k];
+      gd.hi[v] = (uint16_t)swz(x);
+    }
+    for (int j = 0; j < kRegBits; ++j) gd.p[j] = (uint16_t)swz(1u << hg.rs[j]);
+    gd.gate_first = (uint16_t)bgates.size();
+    gd.gate_count = (uint16_t)hg.gates.size();
+    gd.log2_threads = (uint16_t)ndep;
+    bgroups.push_back(gd);
+    for (int k : hg.gates) {
+      const iqsb_fgate &q = in[run[k]];
+      FGate<T> o;
+      memset(&o, 0, sizeof(o));
+      o.m = make_mat<T>(q.m);
+      o.cls = classify(q.m);
+      const int ts = slot_of[q.target];
+      for (int j = 0; j < kRegBits; ++j)
+        if (hg.rs[j] == ts) o.tbit = (uint8_t)j;
+      o.en = 0xF;
+      if (q.kind == 1) {
+        const int cs = slot_of[q.control];
+        if (cs < 0) { o.ckind = 3; o.c = (uint8_t)q.control; }
+        else if (tbit_of[cs] >= 0) { o.ckind = 2; o.c = (uint8_t)tbit_of[cs]; }
+        else {
+          int cb = 0;
+          for (int j = 0; j < kRegBits; ++j)
+            if (hg.rs[j] == cs) cb = j;
+          o.ckind = 1;
+          o.c = (uint8_t)cb;
+          o.en = 0;
+          for (int kk = 0; kk < 4; ++kk) {
+            const int r0 = ((kk >> o.tbit) << (o.tbit + 1)) | (kk & ((1 << o.tbit) - 1));
+            if ((r0 >> cb) & 1) o.en |= (uint8_t)(1u << kk);
+          }
+        }
+      }
+      bgates.push_back(o);
     }
   }
+  flush();
+}
+
+// one run: the gates `run` (indices into `in`, execution order) all have their target in the tile `td`
+template <typename T>
+int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run, const TileDesc &td) {
+  iqsb_ctx *ctx = st->ctx;
+  std::vector<unsigned char> blob;
+  int nbatches = 0;
+  build_batches<T>(in, run, td, blob, nbatches);
+  if (nbatches == 0) return IQSB_OK;
   // descriptors travel through the context's staging ring: written into pinned memory, copied in
   // stream order; the host only waits when the ring wraps around
-  const size_t bytes = sizeof(FGate<T>) * gates.size();
+  const size_t bytes = blob.size();
   if (!ctx->stage_h) {
     IQSB_CUDA(cudaMallocHost((void **)&ctx->stage_h, kStageBytes));
     IQSB_CUDA(cudaMalloc((void **)&ctx->stage_d, kStageBytes));
@@ -258,8 +498,8 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, int first, int last, const 
     IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->stage_off = 0;
   }
-  memcpy(ctx->stage_h + ctx->stage_off, gates.data(), bytes);
-  FGate<T> *d = reinterpret_cast<FGate<T> *>(ctx->stage_d + ctx->stage_off);
+  memcpy(ctx->stage_h + ctx->stage_off, blob.data(), bytes);
+  unsigned char *d = ctx->stage_d + ctx->stage_off;
   IQSB_CUDA(cudaMemcpyAsync(d, ctx->stage_h + ctx->stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stage_off += (bytes + 255) & ~(size_t)255;
   size_t smem = (size_t)sizeof(Cx<T>) << td.nS;
@@ -271,8 +511,77 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, int first, int last, const 
   uint64_t nouter = st->local_amps >> td.nS;
   uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
   unsigned grid = (unsigned)(nouter < cap ? nouter : cap);
-  kernel<<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, (int)gates.size());
+  kernel<<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, nbatches);
   return iqsb_check_launch(ctx, "k_fused");
+}
+
+// The planner.  order = gate indices in execution order, run_end[r] = one past the last entry of
+// run r in `order`, tiles[r*16] = number of tile positions, tiles[r*16 + 1 ..] = the positions.
+int plan_runs(const iqsb_fgate *gates, int ngates, unsigned log2_local, bool reorder, int *order, int *run_end, uint8_t *tiles, int max_runs, int *nruns) {
+  const unsigned K = log2_local < (unsigned)kTile ? log2_local : (unsigned)kTile;
+  const unsigned low = log2_local < (unsigned)kLow ? log2_local : (unsigned)kLow;
+  std::vector<char> done((size_t)ngates, 0);
+  int r = 0, first_pending = 0, nordered = 0;
+  while (nordered < ngates) {
+    IQSB_REQUIRE(r < max_runs, "iqsb_plan_fused: more than %d runs", max_runs);
+    while (done[first_pending]) ++first_pending;
+    bool in[64] = {false};
+    unsigned cnt = 0;
+    for (unsigned b = 0; b < low; ++b) { in[b] = true; ++cnt; }
+    const int run_first = nordered;
+    uint64_t skipped_perm_q = 0, skipped_arith_q = 0;
+    bool arith_skipped = false;
+    int looked = 0;
+    for (int i = first_pending; i < ngates; ++i) {
+      if (done[i]) continue;
+      const iqsb_fgate &g = gates[i];
+      const unsigned t = (unsigned)g.target;
+      IQSB_REQUIRE(t < log2_local, "iqsb_fused: gate %d: target %u is not a local position", i, t);
+      const uint64_t qmask = (1ull << t) | (g.kind == 1 ? 1ull << (unsigned)g.control : 0ull);
+      const bool perm = is_xexact(g.m);
+      // pulled across what was skipped only if that is exact: a permutation commutes without
+      // rounding with gates on other qubits; two arithmetic gates never swap
+      bool ok;
+      if (perm) ok = !(qmask & (skipped_perm_q | skipped_arith_q));
+      else ok = !arith_skipped && !(qmask & skipped_perm_q);
+      const bool fits = in[t] || cnt < K;
+      if (ok && fits) {
+        if (!in[t]) { in[t] = true; ++cnt; }
+        order[nordered++] = i;
+        done[i] = 1;
+        continue;
+      }
+      if (!reorder) break;
+      if (perm) skipped_perm_q |= qmask;
+      else { skipped_arith_q |= qmask; arith_skipped = true; }
+      if (++looked > kReorderWindow) break;
+    }
+    // use the spare slots for controls of the run (cheaper inside the tile), then for low positions
+    for (int k = run_first; k < nordered && cnt < K; ++k) {
+      const iqsb_fgate &g = gates[order[k]];
+      if (g.kind == 1 && (unsigned)g.control < log2_local && !in[g.control]) { in[g.control] = true; ++cnt; }
+    }
+    for (unsigned b = 0; b < log2_local && cnt < K; ++b)
+      if (!in[b]) { in[b] = true; ++cnt; }
+    uint8_t *td = tiles + r * 16;
+    td[0] = (uint8_t)cnt;
+    int n = 0;
+    for (unsigned b = 0; b < log2_local; ++b)
+      if (in[b]) td[1 + n++] = (uint8_t)b;
+    for (; n < 15; ++n) td[1 + n] = 0;
+    run_end[r++] = nordered;
+  }
+  *nruns = r;
+  return IQSB_OK;
+}
+
+bool reorder_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("IQS_B200_FUSED_REORDER");
+    v = (e && *e == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 }  // namespace
@@ -284,44 +593,22 @@ extern "C" int iqsb_fused_max_log2tile(const iqsb_state *st) {
   return k;
 }
 
-// Pure host function: how iqsb_fused cuts a batch into runs.  run_end[r] = index one past the last
-// gate of run r; tiles[r*16] = number of tile positions, tiles[r*16 + 1 ..] = the positions.
+// Pure host function: the in-order cut of a batch into runs (no gate changes place).
 extern "C" int iqsb_plan_fused(const iqsb_fgate *gates, int ngates, unsigned log2_local, int *run_end, uint8_t *tiles, int max_runs, int *nruns) {
   IQSB_REQUIRE((gates || ngates == 0) && run_end && tiles && nruns && max_runs > 0, "iqsb_plan_fused: null argument");
-  const unsigned K = log2_local < (unsigned)kTile ? log2_local : (unsigned)kTile;
-  const unsigned low = log2_local < (unsigned)kLow ? log2_local : (unsigned)kLow;
-  int r = 0, first = 0;
-  while (first < ngates) {
-    IQSB_REQUIRE(r < max_runs, "iqsb_plan_fused: more than %d runs", max_runs);
-    bool in[64] = {false};
-    unsigned cnt = 0;
-    for (unsigned b = 0; b < low; ++b) { in[b] = true; ++cnt; }
-    int last = first;
-    for (; last < ngates; ++last) {
-      unsigned t = (unsigned)gates[last].target;
-      IQSB_REQUIRE(t < log2_local, "iqsb_fused: gate %d: target %u is not a local position", last, t);
-      if (!in[t]) {
-        if (cnt == K) break;
-        in[t] = true;
-        ++cnt;
-      }
-    }
-    // use the spare slots for controls of the run (cheaper inside the tile), then for low positions
-    for (int k = first; k < last && cnt < K; ++k)
-      if (gates[k].kind == 1 && (unsigned)gates[k].control < log2_local && !in[gates[k].control]) { in[gates[k].control] = true; ++cnt; }
-    for (unsigned b = 0; b < log2_local && cnt < K; ++b)
-      if (!in[b]) { in[b] = true; ++cnt; }
-    uint8_t *td = tiles + r * 16;
-    td[0] = (uint8_t)cnt;
-    int n = 0;
-    for (unsigned b = 0; b < log2_local; ++b)
-      if (in[b]) td[1 + n++] = (uint8_t)b;
-    for (; n < 15; ++n) td[1 + n] = 0;
-    run_end[r++] = last;
-    first = last;
-  }
-  *nruns = r;
-  return IQSB_OK;
+  std::vector<int> order((size_t)(ngates > 0 ? ngates : 1));
+  return plan_runs(gates, ngates, log2_local, false, order.data(), run_end, tiles, max_runs, nruns);
+}
+
+// Pure host function: the plan iqsb_fused executes -- exact X / CNOT gates may move ahead of gates
+// on other qubits (reorder != 0); order[] lists the gate indices in execution order.
+extern "C" int iqsb_plan_fused_order(const iqsb_fgate *gates, int ngates, unsigned log2_local, int reorder, int *order, int *run_end, uint8_t *tiles,
+                                     int max_runs, int *nruns) {
+  IQSB_REQUIRE((gates || ngates == 0) && order && run_end && tiles && nruns && max_runs > 0, "iqsb_plan_fused_order: null argument");
+  for (int i = 0; i < ngates; ++i)
+    IQSB_REQUIRE(gates[i].target >= 0 && gates[i].target < 64 && (gates[i].kind != 1 || (gates[i].control >= 0 && gates[i].control < 64)),
+                 "iqsb_plan_fused_order: gate %d has a bad position", i);
+  return plan_runs(gates, ngates, log2_local, reorder != 0, order, run_end, tiles, max_runs, nruns);
 }
 
 extern "C" int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates) {
@@ -336,23 +623,24 @@ extern "C" int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates) {
       IQSB_REQUIRE(gates[i].control >= 0 && (unsigned)gates[i].control < st->log2_local && gates[i].control != gates[i].target,
                    "iqsb_fused: gate %d has bad control", i);
   }
-  if (st->log2_local < 2) {  // nothing to tile
+  if (st->log2_local < (unsigned)kRegBits + 1) {  // nothing to tile
     for (int i = 0; i < ngates; ++i) {
       if (gates[i].kind == 0) IQSB_TRY(iqsb_gate1(st, (unsigned)gates[i].target, gates[i].m, 0, st->local_amps));
       else IQSB_TRY(iqsb_cgate1(st, (unsigned)gates[i].control, (unsigned)gates[i].target, gates[i].m, 0, st->local_amps));
     }
     return IQSB_OK;
   }
-  std::vector<int> run_end((size_t)ngates);
+  std::vector<int> order((size_t)ngates), run_end((size_t)ngates);
   std::vector<uint8_t> tiles((size_t)ngates * 16);
   int nruns = 0;
-  IQSB_TRY(iqsb_plan_fused(gates, ngates, st->log2_local, run_end.data(), tiles.data(), ngates, &nruns));
+  IQSB_TRY(plan_runs(gates, ngates, st->log2_local, reorder_default(), order.data(), run_end.data(), tiles.data(), ngates, &nruns));
   int first = 0;
   for (int r = 0; r < nruns; ++r) {
     TileDesc td;
     td.nS = tiles[r * 16];
     for (int k = 0; k < kTile; ++k) td.pos[k] = tiles[r * 16 + 1 + k];
-    int rc = st->dtype == IQSB_F64 ? launch_run<double>(st, gates, first, run_end[r], td) : launch_run<float>(st, gates, first, run_end[r], td);
+    std::vector<int> run(order.begin() + first, order.begin() + run_end[r]);
+    int rc = st->dtype == IQSB_F64 ? launch_run<double>(st, gates, run, td) : launch_run<float>(st, gates, run, td);
     if (rc != IQSB_OK) return rc;
     first = run_end[r];
   }

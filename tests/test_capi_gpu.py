@@ -401,6 +401,84 @@ def test_small_fused_tiles(gpu_ctx, oracle):
         st.free()
 
 
+def _class_matrices():
+    """one matrix per arithmetic class of the fused kernel (kernels_fused.cu: classify)"""
+    f = 1.0 / math.sqrt(2.0)
+    th = 0.7316
+    c, s = math.cos(th / 2), math.sin(th / 2)
+    return {
+        "general": C.G_FIXED,
+        "real": np.array([c, 0, -s, 0, s, 0, c, 0.0]),  # RY
+        "hadamard": np.array([f, 0, f, 0, f, 0, -f, 0.0]),
+        "rx": np.array([c, 0, 0, -s, 0, -s, c, 0.0]),
+        "diag": np.array([c, -s, 0, 0, 0, 0, c, s]),  # RZ
+        "diag1": np.array([1, 0, 0, 0, 0, 0, f, f]),  # T
+        "z": np.array([1, 0, 0, 0, 0, 0, -1, 0.0]),
+        "anti": np.array([0, 0, 0, -1, 0, 1, 0, 0.0]),  # Y
+        "x": X,
+        "sqrtx": np.array([0.5, 0.5, 0.5, -0.5, 0.5, -0.5, 0.5, 0.5]),
+    }
+
+
+@pytest.mark.parametrize("n", [4, 5, 7, 11, 12, 15, 18])
+def test_fused_gate_classes_and_control_kinds(gpu_ctx, oracle, n):
+    """Every matrix class (exact zeros / ones left out of the arithmetic) with no control, a control
+    inside the group's register bits, inside the tile and outside the tile; long runs (several
+    descriptor batches); tiles smaller than 2^12.  Value-identical to the gate-by-gate oracle."""
+    mats = list(_class_matrices().values())
+    rng = np.random.Generator(np.random.MT19937(100 + n))
+    st = gpu_ctx.alloc(1 << n)
+    psi = C.random_state(n, seed=n)
+    for trial in range(3):
+        st.upload(psi)
+        ref = psi.copy()
+        gates = []
+        ngates = (40, 130, 260)[trial]
+        span = (min(n, 4), min(n, 12), n)[trial]  # all targets in a few bits -> deep groups; anywhere -> many runs
+        for i in range(ngates):
+            m = mats[int(rng.integers(0, len(mats)))]
+            t = int(rng.integers(0, span))
+            if rng.integers(0, 2):
+                gates.append((0, 0, t, m))
+                oracle.gate1(ref, t, m)
+            else:
+                c = int(rng.integers(0, n))
+                while c == t:
+                    c = int(rng.integers(0, n))
+                gates.append((1, c, t, m))
+                oracle.cgate1(ref, c, t, m)
+        st.fused(gates)
+        got = st.download()
+        assert np.array_equal(got, ref), f"n={n} trial={trial} maxdiff={np.max(np.abs(got - ref))}"
+    st.free()
+
+
+def test_fused_layered_circuit_reordered_plan_is_bit_exact(gpu_ctx, oracle):
+    """The bench circuit (1-qubit gates from the named set + CNOT ladder): CNOTs float into earlier
+    runs (iqsb_plan_fused_order), the state equals the program-order oracle bit for bit."""
+    n = 20
+    prog = C.layered_random(n, 3, seed=5)
+    st = gpu_ctx.alloc(1 << n)
+    psi = C.random_state(n, seed=9)
+    st.upload(psi)
+    ref, _, _ = oracle.run_program(n, psi.copy(), prog.ops)
+    import bench
+
+    gates = []
+    for op in prog.ops:
+        m = bench.named_matrix(C, int(op["kind"]), op["p"])
+        if op["kind"] == C.CX:
+            gates.append((1, int(op["q0"]), int(op["q1"]), m))
+        else:
+            gates.append((0, 0, int(op["q0"]), m))
+    plan = capi.plan_fused_order(gates, n)
+    assert [i for run, _ in plan for i in run] != list(range(len(gates)))  # something did move
+    assert len(plan) < len(capi.plan_fused(gates, n))
+    st.fused(gates)
+    assert np.array_equal(st.download(), ref)
+    st.free()
+
+
 def test_float_register_within_float_tolerance(gpu_ctx, oracle):
     """ComplexSP rides the same kernels: checked against the double oracle."""
     n = 10

@@ -58,3 +58,58 @@ def test_controls_prefer_tile_slots():
     gates = [(1, 30, 5, X), (1, 29, 6, X)]
     (first, last, tile), = capi.plan_fused(gates, 32)
     assert 30 in tile and 29 in tile  # spare slots are given to the controls of the run
+
+
+# ---- the plan iqsb_fused executes: exact X / CNOT gates may move ahead of gates on other qubits ----
+def _qubits(g):
+    return {g[2]} | ({g[1]} if g[0] == 1 else set())
+
+
+def _is_perm(g):
+    return np.array_equal(np.asarray(g[3], dtype=float), X)
+
+
+def check_order(gates, plan, M):
+    order = [i for run, _ in plan for i in run]
+    assert sorted(order) == list(range(len(gates)))  # every gate exactly once
+    when = {i: k for k, i in enumerate(order)}
+    for run, tile in plan:
+        assert tile == sorted(set(tile)) and len(tile) == min(K, M)
+        for i in run:
+            assert gates[i][2] in tile
+    for i in range(len(gates)):
+        for j in range(i + 1, len(gates)):
+            if when[j] < when[i]:  # j overtook i: allowed only if that is exact
+                assert not (_qubits(gates[i]) & _qubits(gates[j])), (i, j)
+                assert _is_perm(gates[i]) or _is_perm(gates[j]), (i, j)
+
+
+def test_cnots_float_into_the_run_of_their_qubits():
+    """a layer of 32 one-qubit gates + 16 CNOTs: 4 sweeps (6 in program order), for both CNOT parities"""
+    for parity in (0, 1):
+        gates = [(0, 0, q, H) for q in range(32)] + [(1, q, q + 1, X) for q in range(parity, 31, 2)]
+        plan = capi.plan_fused_order(gates, 32)
+        check_order(gates, plan, 32)
+        assert len(plan) == 4
+        assert len(capi.plan_fused_order(gates, 32, reorder=False)) == len(capi.plan_fused(gates, 32)) == 6
+
+
+def test_without_reorder_the_plan_is_the_program_order():
+    rng = np.random.default_rng(3)
+    gates = [(int(rng.integers(0, 2)), int(c), int(t), X if rng.integers(0, 2) else H) for c, t in (rng.permutation(20)[:2] for _ in range(150))]
+    plan = capi.plan_fused_order(gates, 20, reorder=False)
+    assert [i for run, _ in plan for i in run] == list(range(len(gates)))
+    assert [(len(run), tile) for run, tile in plan] == [(last - first, tile) for first, last, tile in capi.plan_fused(gates, 20)]
+
+
+def test_reordered_plans_respect_exact_commutation():
+    rng = np.random.default_rng(11)
+    for M in (5, 13, 20, 33):
+        gates = []
+        for i in range(160):
+            c, t = (int(x) for x in rng.permutation(M)[:2])
+            kind = int(rng.integers(0, 2))
+            gates.append((kind, c, t, X if rng.integers(0, 3) else H))
+        plan = capi.plan_fused_order(gates, M)
+        check_order(gates, plan, M)
+        assert len(plan) <= len(capi.plan_fused(gates, M))

@@ -100,8 +100,23 @@ def main():
             timeit(f"fused_hi{ng}", "-", lambda gates=gates: st.fused(gates), 32.0 * L)
         # a layer of one-qubit gates on every qubit followed by a CX chain (several runs)
         gates = [(0, 0, q, C.G_FIXED) for q in range(n)] + [(1, q, q + 1, X) for q in range(0, n - 1, 2)]
-        runs = len(capi.plan_fused(gates, n))
+        runs = len(capi.plan_fused_order(gates, n))
         timeit(f"fused_layer{len(gates)}g{runs}r", "-", lambda gates=gates: st.fused(gates), 32.0 * L * runs)
+        # in-tile cost per matrix class: 12 / 48 gates on the 12 lowest positions (one run)
+        f, c_, s_ = 1 / math.sqrt(2), math.cos(0.4), math.sin(0.4)
+        classes = {"general": C.G_FIXED, "real": H, "rx": np.array([c_, 0, 0, -s_, 0, -s_, c_, 0.0]), "diag": np.array([c_, -s_, 0, 0, 0, 0, c_, s_]),
+                   "diag1": np.array([1, 0, 0, 0, 0, 0, f, f]), "x": X}
+        for cname, m in classes.items():
+            for ng in (12, 48):
+                gates = [(0, 0, i % 12, m) for i in range(ng)]
+                timeit(f"fused{ng}_{cname}", "-", lambda gates=gates: st.fused(gates), 32.0 * L)
+        # the layers bench.py times (named 1-qubit gates + CNOT ladder), one call per layer
+        import bench
+
+        for li, layer in enumerate(bench.build_layers(C, n, 2)):
+            gates = [((1, int(op["q0"]), int(op["q1"])) if op["kind"] == C.CX else (0, 0, int(op["q0"]))) + (bench.named_matrix(C, int(op["kind"]), op["p"]),) for op in layer]
+            runs = len(capi.plan_fused_order(gates, n))
+            timeit(f"bench_layer{li}_{len(gates)}g{runs}r", "-", lambda gates=gates: st.fused(gates), 32.0 * L * runs)
     if "gate2" in ops:
         rng = np.random.default_rng(0)
         q, _ = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))

@@ -8,14 +8,21 @@ A "step" is one layer.  N = 1: 32 qubits (64 GiB state in HBM).  N > 1 (weak sca
 qubits per GPU, 32 + log2(N) qubits in total, so the top log2(N) qubits are global and their gates
 run as fused compute+exchange kernels over NVLink peer memory.
 
+Every GPU leg goes through the drop-in API a user of the reference calls: iqs::QubitRegister<ComplexDP>
+(libiqs.so, bound as the pybind11 module `intelqs_py`), which dispatches to the C ABI / CUDA kernels.
+
 metric / value : effective GB/s = algorithmic bytes of the step (32 B x 2^n for a
-                 1-qubit gate, 16 B x 2^n for a controlled gate) / device time, aggregated over ranks.
-                 gates/s is reported next to it (`gates_per_s`).
-e2e            : the same metric through the public API a user calls -- the pybind11 module
-                 `intelqs_py` over iqs::QubitRegister<ComplexDP> -- with the gate matrices as host
-                 numpy buffers every step and a GetProbability() read-back closing each step.
+                 1-qubit gate, 16 B x 2^n for a controlled gate) / device time (CUDA events on the
+                 engine's stream, max over ranks), aggregated over ranks; the state is resident in
+                 HBM, gates are applied one by one (no fusion).  gates/s next to it (`gates_per_s`).
+e2e            : the same steps with the gate matrices as host numpy buffers every step and a
+                 GetProbability() read-back closing each step, timed by the host clock too;
+                 e2e.fused: the same under TurnOnFusion() (the reference's own switch).
 roofline       : dense 1-qubit gate kernel (k_pairs_w2<double>): 32 B x 2^M per launch / its mean
-                 launch duration measured with CUDA events inside the timed region.
+                 launch duration, from the engine's per-kernel-class CUDA events (iqsb_profile)
+                 recorded INSIDE the timed region of the `value` leg.
+roofline_nvlink: (N > 1) the multi-bit qubit exchange kernel of the placement layer: bytes per
+                 rank and direction / its mean duration, against 900 GB/s.
 cpu_baseline   : the UNMODIFIED reference (oracle/_ref/iqs_ref_driver, OpenMP on all host cores)
                  on a bounded sample of the same circuit.
 --impl reference times that reference build as its own arm.
@@ -37,7 +44,23 @@ import __graft_entry__ as entry  # noqa: E402
 
 SEED = 20971
 LOCAL_QUBITS = 32
-CPU_SAMPLE_QUBITS = int(os.environ.get("IQS_BENCH_CPU_QUBITS", "29"))
+
+
+def cpu_sample_qubits():
+    """Largest register (<= 31 qubits) the host's free RAM holds twice over; IQS_BENCH_CPU_QUBITS overrides."""
+    if os.environ.get("IQS_BENCH_CPU_QUBITS"):
+        return int(os.environ["IQS_BENCH_CPU_QUBITS"])
+    avail = 0
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    n = 26
+    while n < 31 and 16 * (1 << (n + 1)) * 2 + (8 << 30) <= avail:
+        n += 1
+    return n
 
 
 _STDOUT_FD = None
@@ -127,53 +150,6 @@ def layer_bytes(C, layer, n_total):
     return b
 
 
-class Engine:
-    """Position-level dispatch over the C ABI (identity qubit map), mirroring what
-    QubitRegister::Apply1QubitGate_helper / ApplyControlled1QubitGate_helper do in C++."""
-
-    def __init__(self, capi, C, ctx, st, M, rank, nranks):
-        self.capi, self.C, self.ctx, self.st, self.M, self.rank, self.nranks = capi, C, ctx, st, M, rank, nranks
-
-    def gate1(self, pos, m):
-        if pos < self.M:
-            self.st.gate1(pos, m)
-            return "dense1"
-        diag = m[2] == 0 and m[3] == 0 and m[4] == 0 and m[5] == 0
-        if diag:
-            bit = (self.rank >> (pos - self.M)) & 1
-            self.st.scale(complex(m[6], m[7]) if bit else complex(m[0], m[1]))
-            return "scale"
-        self.st.gate1_global(self.M, pos, m)
-        return "global1"
-
-    def cgate1(self, c, t, m):
-        M = self.M
-        if c < M and t < M:
-            self.st.cgate1(c, t, m)
-            return "ctrl"
-        if c >= M and t < M:
-            if (self.rank >> (c - M)) & 1:
-                self.st.gate1(t, m)
-            return "ctrl_gc"
-        if c >= M and t >= M:
-            if (self.rank >> (c - M)) & 1:
-                self.st.gate1_global(M, t, m)
-            else:
-                self.st.idle_global()
-            return "global_cc"
-        self.st.cgate1_global(M, c, t, m)
-        return "global_ct"
-
-    def run_layer(self, layer, mats, record=None):
-        """record(slot_name) is called between groups so the caller can time the dense 1q block."""
-        C = self.C
-        for op, m in zip(layer, mats):
-            if op["kind"] == C.CX:
-                self.cgate1(int(op["q0"]), int(op["q1"]), m)
-            else:
-                self.gate1(int(op["q0"]), m)
-
-
 # ---------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------
@@ -225,12 +201,17 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the unmodified reference through its own public API
 # ---------------------------------------------------------------------------------------------
-def run_reference_steps(C, n, nsteps):
-    """Time `nsteps` layers of the circuit at `n` qubits with oracle/_ref/iqs_ref_driver.
-    Returns (list of per-step seconds, list of per-step algorithmic bytes, gates per step, kind, cores)."""
+def run_reference_steps(C, n, nsteps, gates_per_step=None, spec_v2=False):
+    """Time `nsteps` steps of the circuit at `n` qubits with oracle/_ref/iqs_ref_driver.  A step is
+    a layer, or its first `gates_per_step` gates (bounded sample).
+    Returns (per-step seconds, per-step algorithmic bytes, per-step gate counts, kind, cores)."""
     orc = entry.load_oracle()
     layers = build_layers(C, n, nsteps)
+    if gates_per_step:
+        layers = [L[:gates_per_step] for L in layers]
     prog = C.Program(n)
+    if spec_v2:
+        prog.mode(C.SPEC2_ON)
     for L in layers:
         for op in L:
             prog._ops.append(op)
@@ -243,8 +224,10 @@ def run_reference_steps(C, n, nsteps):
             pf = os.path.join(td, "prog.bin")
             prog.write(pf, init=2)
             env = dict(os.environ, OMP_NUM_THREADS=str(cores), OMP_PROC_BIND="close", OMP_PLACES="cores")
-            sizes = ",".join(str(len(L)) for L in layers)
-            r = subprocess.run([orc.REF_DRIVER, pf, "--step-sizes", sizes], env=env, capture_output=True, text=True)
+            sizes = [len(L) for L in layers]
+            if spec_v2:
+                sizes[0] += 1  # the mode switch rides with the first (warm-up) step
+            r = subprocess.run([orc.REF_DRIVER, pf, "--step-sizes", ",".join(str(x) for x in sizes), "--no-step-norm"], env=env, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("reference driver failed: " + r.stderr[-2000:])
             secs = [float(l.split()[2]) for l in r.stdout.splitlines() if l.startswith("STEP ")]
@@ -262,25 +245,39 @@ def run_reference_steps(C, n, nsteps):
     return secs, nbytes, gates, kind, cores
 
 
+def reference_budget(n, nsteps, seconds):
+    """gates per step so that `nsteps` steps at n qubits take about `seconds` on a ~130 GB/s host"""
+    per_gate = 32.0 * float(1 << n) / 110e9
+    g = int(seconds / max(1, nsteps) / per_gate)
+    return max(4, min(g, n + n // 2))
+
+
 def reference_arm(args, C):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = CPU_SAMPLE_QUBITS
+    n = cpu_sample_qubits()
     total = args.warmup + args.steps
-    secs, nbytes, gates, kind, cores = run_reference_steps(C, n, total)
-    secs_t, bytes_t, gates_t = secs[args.warmup :], nbytes[args.warmup :], gates[args.warmup :]
-    T = sum(secs_t)
-    gbs = sum(bytes_t) / T / 1e9
-    sample = (f"{args.steps} layers of the same layered random circuit at {n} qubits ({16 * (1 << n) / 2**30:.0f} GiB state) instead of {LOCAL_QUBITS}; "
-              "effective GB/s is size-independent for this bandwidth-bound path, gates/s at 32 qubits = gates_per_s_sample / 2^(32-%d)" % n)
+    g = reference_budget(n, 2 * total, 200.0)  # two passes (generic path, TurnOnSpecializeV2) in ~200 s
+    res = {}
+    for name, spec in (("generic", False), ("specialize_v2", True)):
+        secs, nbytes, gates, kind, cores = run_reference_steps(C, n, total, gates_per_step=g, spec_v2=spec)
+        secs_t, bytes_t, gates_t = secs[args.warmup:], nbytes[args.warmup:], gates[args.warmup:]
+        T = sum(secs_t)
+        res[name] = {"GBps": sum(bytes_t) / T / 1e9, "gates_per_s_sample": sum(gates_t) / T, "seconds": T, "gates": sum(gates_t)}
+    best = max(res, key=lambda k: res[k]["GBps"])
+    gbs, T = res[best]["GBps"], res[best]["seconds"]
+    sample = (f"{args.steps} steps, each the first {g} gates of a layer of the same layered random circuit, at {n} qubits ({16 * (1 << n) / 2**30:.0f} GiB state) "
+              f"instead of {LOCAL_QUBITS}: what the host's RAM and a few minutes allow; effective GB/s is size-independent for this bandwidth-bound path. "
+              f"value = the faster of the reference's generic path and TurnOnSpecializeV2() ({best})")
     out = {
         "impl": "reference", "metric": "effective_GBps", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * T / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "layered random 1q+CNOT circuit, ComplexDP (BASELINE configs[1])", "qubits_sampled": n, "qubits_target": LOCAL_QUBITS,
-                   "gates_per_step": float(np.mean(gates_t)), "timing": "wall clock around QubitRegister calls, state larger than LLC"},
-        "gates_per_s_sample": sum(gates_t) / T,
-        "gates_per_s_at_32q_extrapolated": sum(gates_t) / T / float(1 << (LOCAL_QUBITS - n)),
+                   "gates_per_step": float(g), "timing": "wall clock around QubitRegister calls, state larger than LLC"},
+        "gates_per_s_sample": res[best]["gates_per_s_sample"],
+        "gates_per_s_at_32q_extrapolated": res[best]["gates_per_s_sample"] / float(1 << (LOCAL_QUBITS - n)),
+        "paths": res,
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -291,6 +288,20 @@ def reference_arm(args, C):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def ncu_traffic(M):
+    """dram read+write bytes per launch of the dominant kernel, from this round's `ncu --set full`
+    capture (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the committed .ncu-rep)."""
+    for name in ("r02_traffic.json", "traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if "dram_bytes_per_launch" in t:
+                return t["dram_bytes_per_launch"] * (float(1 << M) / float(1 << t["qubits"])), t.get("source")
+            return t["k_pairs_w2_bytes_per_launch_32q"] * (float(1 << M) / float(1 << 32)), name
+        except Exception:
+            continue
+    return None, None
+
+
 def gpu_arm(args, pkg):
     capi, C = pkg.capi, pkg.circuits
     rank = int(os.environ.get("RANK", "0"))
@@ -309,12 +320,6 @@ def gpu_arm(args, pkg):
 
     M = args.local_qubits
     n = M + int(math.log2(world))
-    uid = None
-    if world > 1:
-        box = [capi.unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        uid = box[0]
-    ctx = capi.Context(rank, world, uid, device=local_rank if world > 1 else -1)
 
     def all_max(x):
         if world == 1:
@@ -325,173 +330,164 @@ def gpu_arm(args, pkg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sys.path.insert(0, os.path.join(ROOT, "intel-qs_b200", "lib"))
+    import intelqs_py as iqs  # no fallback: a missing CUDA extension is an ImportError here
+
+    uid = bcast_uid(dist, capi, rank) if world > 1 else b""
+    iqs.EnvInitWithUniqueId(rank, world, uid, local_rank if world > 1 else -1)
+
     def barrier():
-        ctx.sync()
+        iqs.DeviceSync()
         if world > 1:
             dist.barrier()
 
     total = args.warmup + args.steps
     layers = build_layers(C, n, total)
     mats = [[named_matrix(C, int(op["kind"]), op["p"]) for op in L] for L in layers]
+    cm = [[np.ascontiguousarray(m.view(np.complex128).reshape(2, 2)) for m in Ms] for Ms in mats]
     peak, peak_kind = measured_peaks()
+    job_bytes = sum(layer_bytes(C, layers[s], n) for s in range(args.warmup, total))
+    job_gates = sum(len(layers[s]) for s in range(args.warmup, total))
 
-    # ---------------- device-resident run through the C ABI ----------------
-    st = ctx.alloc(1 << M)
-    if world > 1:
-        st.share()
-    st.fill_const(1.0 / math.sqrt(float(1 << n)))
-    eng = Engine(capi, C, ctx, st, M, rank, world)
+    psi = iqs.QubitRegister(n, "++++", 0, 0)
+
+    def apply_layer(L, Ms):
+        for op, m in zip(L, Ms):
+            if op["kind"] == C.CX:
+                psi.ApplyControlled1QubitGate(int(op["q0"]), int(op["q1"]), m)
+            else:
+                psi.Apply1QubitGate(int(op["q0"]), m)
+
+    # ---------------- value: device-timed, gate by gate, state resident ----------------
     for w in range(args.warmup):
-        eng.run_layer(layers[w], mats[w])
+        apply_layer(layers[w], cm[w])
+    psi.ApplyFusedGates()  # nothing stays queued (with several GPUs gates wait for the placement look-ahead)
     barrier()
     sampler = ClockSampler(local_rank if world > 1 else 0)
     if rank == 0:
         sampler.start()
-    launches0 = ctx.launches()
-    nv0 = ctx.nvlink_bytes()
-    slot = 0
-    dense_pairs = []  # (slot_a, slot_b, launches) around runs of dense local 1-qubit gates
-    ctx.event_record(slot)
-    t_begin = slot
+    launches0, nv0 = iqs.LaunchCount(), iqs.NvlinkBytes()
+    iqs.DeviceProfile(True)
+    iqs.DeviceTimerStart()
     for s in range(args.warmup, total):
-        L, Ms = layers[s], mats[s]
-        # the local 1-qubit gates of the layer form one contiguous block: bracket it with events
-        local1 = [(op, m) for op, m in zip(L, Ms) if op["kind"] != C.CX and int(op["q0"]) < M]
-        rest = [(op, m) for op, m in zip(L, Ms) if not (op["kind"] != C.CX and int(op["q0"]) < M)]
-        a = slot
-        for op, m in local1:
-            st.gate1(int(op["q0"]), m)
-        slot += 1
-        ctx.event_record(slot)
-        dense_pairs.append((a, slot, len(local1)))
-        for op, m in rest:
-            if op["kind"] == C.CX:
-                eng.cgate1(int(op["q0"]), int(op["q1"]), m)
-            else:
-                eng.gate1(int(op["q0"]), m)
-        slot += 1
-        ctx.event_record(slot)
-    t_end = slot
+        apply_layer(layers[s], cm[s])
+    psi.ApplyFusedGates()
+    ms_total = all_max(iqs.DeviceTimerStop())
+    iqs.DeviceProfile(False)
+    prof = {c["name"]: c for c in json.loads(iqs.DeviceProfileRead())["classes"]}
     barrier()
-    ms_total = all_max(ctx.event_elapsed(t_begin, t_end))
     clocks = sampler.stop() if rank == 0 else None
-    launches = ctx.launches() - launches0
-    nvlink = ctx.nvlink_bytes() - nv0
-    dense_ms = sum(ctx.event_elapsed(a, b) for a, b, _ in dense_pairs)
-    dense_launches = sum(k for _, _, k in dense_pairs)
-    job_bytes = sum(layer_bytes(C, layers[s], n) for s in range(args.warmup, total))
-    job_gates = sum(len(layers[s]) for s in range(args.warmup, total))
+    launches = iqs.LaunchCount() - launches0
+    nvlink = iqs.NvlinkBytes() - nv0
     value = job_bytes / (ms_total * 1e-3) / 1e9
-    # roofline of the dominant kernel: algorithmic 32 B x 2^M per launch on this GPU
-    per_launch_ms = dense_ms / max(1, dense_launches)
-    achieved = 32.0 * float(1 << M) / (per_launch_ms * 1e-3) / 1e9
-    norm_after = st.norm2()
+    dense = prof.get("k_pairs_dense1", {"launches": 0, "ms": 0.0})
+    per_launch_ms = dense["ms"] / max(1, dense["launches"])
+    achieved = 32.0 * float(1 << M) / (per_launch_ms * 1e-3) / 1e9 if dense["launches"] else 0.0
+    roof_nv = None
     if world > 1:
-        norm_after = float(ctx.allreduce([norm_after])[0])
-    st.free()
+        x = prof.get("k_exchange")
+        if x and x["launches"]:
+            a = x["bytes"] / (x["ms"] * 1e-3) / 1e9
+            a = all_max(-a) * -1.0  # the slowest rank
+            roof_nv = {"bound": "nvlink", "kernel": "k_exchange (k local <-> k global qubits in one pass over peer memory, loads one way and stores the other)",
+                       "achieved": a, "peak": 900.0, "unit": "GB/s per GPU per direction", "frac": a / 900.0, "peak_kind": "nominal NVLink 5 (18 links x 50 GB/s)",
+                       "launches_timed": x["launches"], "ms_per_launch": x["ms"] / x["launches"], "bytes_per_rank_per_dir_per_launch": x["bytes"] / x["launches"],
+                       "traffic": None}
+    t0 = time.perf_counter()
+    iqs.MPIEnvironment.StateBarrier()  # back to the reference's amplitude order (only needed before the host reads amplitudes)
+    restore_ms = all_max(1e3 * (time.perf_counter() - t0))
+    norm_after = float(psi.ComputeNorm()) ** 2
 
-    # ---------------- end to end through the public API (pybind11 QubitRegister) ----------------
+    # ---------------- end to end: host matrices every step + a read-back closing each step ----------------
     e2e = None
     try:
-        sys.path.insert(0, os.path.join(ROOT, "intel-qs_b200", "lib"))
-        import intelqs_py as iqs
-
-        uid2 = bcast_uid(dist, capi, rank) if world > 1 else b""
-        iqs.EnvInitWithUniqueId(rank, world, uid2, local_rank if world > 1 else -1)
-        psi = iqs.QubitRegister(n, "++++", 0, 0)
-        cm = [[np.ascontiguousarray(m.view(np.complex128).reshape(2, 2)) for m in Ms] for Ms in mats]
-
         def api_layer(L, Ms):
-            for op, m in zip(L, Ms):
-                if op["kind"] == C.CX:
-                    psi.ApplyControlled1QubitGate(int(op["q0"]), int(op["q1"]), m)
-                else:
-                    psi.Apply1QubitGate(int(op["q0"]), m)
+            apply_layer(L, Ms)
             return psi.GetProbability(0)  # the step's result: one double read back from the device
 
-        for w in range(args.warmup):
-            api_layer(layers[w], cm[w])
-        iqs.MPIEnvironment.StateBarrier()
-        if world > 1:
-            dist.barrier()
-        iqs.DeviceTimerStart()
-        t0 = time.perf_counter()
-        for s in range(args.warmup, total):
-            api_layer(layers[s], cm[s])
-        ms_dev = iqs.DeviceTimerStop()
-        wall = time.perf_counter() - t0
-        t_e2e = all_max(max(wall, ms_dev * 1e-3))
-        e2e = {"value": job_bytes / t_e2e / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": int(64 * job_gates / args.steps), "d2h_bytes_per_step": 8,
-               "gates_per_s": job_gates / t_e2e, "api": "intelqs_py.QubitRegister.Apply1QubitGate/ApplyControlled1QubitGate(numpy 2x2) + GetProbability",
-               "note": "the state stays resident in HBM like the reference's stays in RAM; per-step host inputs are the gate matrices"}
-        # the same steps with gate fusion on (TurnOnFusion): reported next to the headline, not as it
-        def fused_leg():
-            psi.TurnOnFusion(11)
-            api_layer(layers[0], cm[0])
-            iqs.MPIEnvironment.StateBarrier()
-            if world > 1:
-                dist.barrier()
+        def timed_leg():
+            for w in range(args.warmup):
+                api_layer(layers[w], cm[w])
+            barrier()
             iqs.DeviceTimerStart()
             t0 = time.perf_counter()
             for s in range(args.warmup, total):
                 api_layer(layers[s], cm[s])
             ms_dev = iqs.DeviceTimerStop()
-            t_f = all_max(max(time.perf_counter() - t0, ms_dev * 1e-3))
+            wall = time.perf_counter() - t0
+            return all_max(max(wall, ms_dev * 1e-3))
+
+        t_e2e = timed_leg()
+        e2e = {"value": job_bytes / t_e2e / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": int(64 * job_gates / args.steps), "d2h_bytes_per_step": 8,
+               "gates_per_s": job_gates / t_e2e, "api": "intelqs_py.QubitRegister.Apply1QubitGate/ApplyControlled1QubitGate(numpy 2x2) + GetProbability",
+               "note": "the state stays resident in HBM like the reference's stays in RAM; per-step host inputs are the gate matrices"}
+
+        def fused_leg():
+            psi.TurnOnFusion(11)
+            iqs.DeviceProfile(True)
+            t = timed_leg()
+            iqs.DeviceProfile(False)
             psi.TurnOffFusion()
-            return {"value": job_bytes / t_f / 1e9, "unit": "GB/s", "gates_per_s": job_gates / t_f}
+            cls = {c["name"]: {"launches": c["launches"], "ms": round(c["ms"], 3)} for c in json.loads(iqs.DeviceProfileRead())["classes"]}
+            return {"value": job_bytes / t / 1e9, "unit": "GB/s", "gates_per_s": job_gates / t, "ms_per_step": 1e3 * t / args.steps,
+                    "kernel_classes_incl_warmup": cls}
 
         try:
             e2e["fused"] = fused_leg()
-            e2e["fused"]["note"] = "TurnOnFusion(): runs of gates share one HBM sweep (shared-memory tiles built from arbitrary qubit positions); exact arithmetic, bit-identical results"
+            e2e["fused"]["note"] = ("TurnOnFusion(): runs of gates share one HBM sweep (shared-memory tiles built from arbitrary qubit positions, gates applied in "
+                                    "registers three tile bits at a time); exact arithmetic, results identical to gate by gate")
             iqs.SetContractedArithmetic(True)
             e2e["fused_fma"] = fused_leg()
             e2e["fused_fma"]["note"] = "same with IQSB_ARITH_FMA (opt-in, like the reference's IqsNative=ON build): results agree to ~1e-16"
             iqs.SetContractedArithmetic(False)
         except Exception as exc:
             log(f"[bench] fused leg failed: {exc!r}")
-        del psi
-        iqs.EnvFinalize()
     except Exception as exc:  # the end-to-end leg must never hide the device-side number
         log(f"[bench] e2e leg failed: {exc!r}")
+    del psi
+    iqs.EnvFinalize()
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            secs, nbytes, gates, kind, cores = run_reference_steps(C, CPU_SAMPLE_QUBITS, 2)
+            nc = cpu_sample_qubits()
+            g = reference_budget(nc, 2, 20.0)
+            secs, nbytes, gates, kind, cores = run_reference_steps(C, nc, 2, gates_per_step=g)
             cpu = {"value": nbytes[1] / secs[1] / 1e9, "unit": "GB/s", "cores": cores, "kind": kind,
                    "gates_per_s_sample": gates[1] / secs[1],
-                   "sample": f"2nd of 2 layers of the same circuit at {CPU_SAMPLE_QUBITS} qubits ({16 * (1 << CPU_SAMPLE_QUBITS) / 2**30:.0f} GiB state), OpenMP on all host cores; GB/s is size-independent for this bandwidth-bound path"}
+                   "sample": f"the first {g} gates of the 2nd of 2 layers of the same circuit at {nc} qubits ({16 * (1 << nc) / 2**30:.0f} GiB state), OpenMP on all host cores; GB/s is size-independent for this bandwidth-bound path"}
         except Exception as exc:
             log(f"[bench] cpu baseline failed: {exc!r}")
 
     if rank == 0:
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_pairs_w2_bytes_per_launch_32q"] * (float(1 << M) / float(1 << 32))
-        except Exception:
-            pass
+        traffic, traffic_src = ncu_traffic(M)
         out = {
             "metric": "effective_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "layered random 1q+CNOT circuit, ComplexDP (BASELINE configs[1])", "qubits": n, "local_qubits_per_gpu": M,
                        "gates_per_step": job_gates / args.steps, "state_bytes_per_gpu": 16 * (1 << M),
                        "l2": "state (64 GiB) is ~500x larger than L2: no flush needed", "timing": "CUDA events on the engine stream, max over ranks",
-                       "partition": "rank r owns amplitudes [r*2^M,(r+1)*2^M); top log2(N) qubits are global (peer-memory kernels over NVLink)"},
+                       "api": "iqs::QubitRegister<ComplexDP> through intelqs_py, one call per gate, fusion off",
+                       "partition": "rank r owns amplitudes [r*2^M,(r+1)*2^M); the top log2(N) qubits are rank bits; the placement layer swaps a qubit a gate needs "
+                                    "into a local bit (multi-bit exchange over NVLink peer memory) and keeps it there"},
             "gates_per_s": job_gates / (ms_total * 1e-3),
             "roofline": {"bound": "hbm", "kernel": "k_pairs_w2<double> (dense 1-qubit gate, 256-bit loads/stores)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_kind": peak_kind, "traffic": traffic, "launches_timed": dense_launches, "ms_per_launch": per_launch_ms,
-                         "algorithmic_bytes_per_launch": 32.0 * float(1 << M)},
+                         "frac": achieved / peak, "peak_kind": peak_kind, "traffic": traffic, "traffic_source": traffic_src, "launches_timed": dense["launches"],
+                         "ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": 32.0 * float(1 << M)},
+            "kernel_classes": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in prof.items()},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "nvlink_bytes_per_rank": int(nvlink),
+            "placement_restore_ms": restore_ms,
             "clocks": clocks,
             "norm2_after": norm_after,
         }
+        if roof_nv:
+            out["roofline_nvlink"] = roof_nv
         emit(out)
-    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -76,6 +76,13 @@ int iqsb_set_arith(iqsb_ctx *ctx, int mode);
 int iqsb_get_arith(const iqsb_ctx *ctx);
 /* number of kernels this context launched since creation (bench.py: gpu_launches). */
 uint64_t iqsb_launch_count(const iqsb_ctx *ctx);
+/* Per-kernel-class device timing with CUDA events on the engine's stream (what bench.py's roofline
+ * block is computed from; the reference's counterpart is the Timer of include/timer.hpp, filled by
+ * QubitRegister::EnableStatistics).  iqsb_profile(ctx, 1) clears and starts, iqsb_profile(ctx, 0)
+ * stops; iqsb_profile_read writes JSON text {"overflow": bool, "classes": [{"name", "launches",
+ * "ms", "bytes" (algorithmic bytes, 0 if not stated)}]} into out[cap]. */
+int iqsb_profile(iqsb_ctx *ctx, int on);
+int iqsb_profile_read(iqsb_ctx *ctx, char *out, size_t cap);
 /* device-side timing on the context's stream (CUDA events). */
 int iqsb_timer_start(iqsb_ctx *ctx);
 int iqsb_timer_stop(iqsb_ctx *ctx, double *elapsed_ms);
@@ -175,6 +182,17 @@ int iqsb_plan_fused_order(const iqsb_fgate *gates, int ngates, unsigned log2_loc
 int iqsb_prob1(iqsb_state *st, unsigned pos, double *out);
 /* sum_i (-1)^popcount((glb_start+i) & mask) |a_i|^2: ExpectationValue (src/qureg_expectval.cpp:173-185) */
 int iqsb_parity_expect(iqsb_state *st, uint64_t mask, uint64_t glb_start, double *out);
+/* All marginals in ONE read of the shard: out[0] = sum |a|^2, out[1 + q] = sum of |a_i|^2 over local
+ * indices with bit q set, q < log2(local_amps); nout >= 1 + log2(local_amps).  n calls of
+ * GetProbability (src/qureg_measure.cpp:135-178) cost one sweep instead of n. */
+int iqsb_prob_all(iqsb_state *st, double *out, int nout);
+/* Read-only expectation value of a Pauli string: X on the bits of xmask, Y on ymask, Z on zmask
+ * (masks over the GLOBAL index; X / Y bits must be local positions, Z bits may be rank bits, taken
+ * from glb_start).  Replaces the basis-change sweeps of ExpectationValue
+ * (src/qureg_expectval.cpp:148-210: 2k gate sweeps + 1 read) by one read; the state is not touched.
+ * out[0] = the expectation value (local part), out[1] = sum |a|^2 of the shard from the same read:
+ * the reference's 1-qubit wrappers return 1 - 2 P(1) = <P> + (1 - norm^2) (src/qureg_expectval.cpp:18-66). */
+int iqsb_pauli_expect(iqsb_state *st, uint64_t xmask, uint64_t ymask, uint64_t zmask, uint64_t glb_start, double out[2]);
 /* sum |a|^2: ComputeNorm before sqrt (src/qureg_utils.cpp:236-255) */
 int iqsb_norm2(iqsb_state *st, double *out);
 /* sum conj(b_i) a_i: ComputeOverlap (src/qureg_utils.cpp:259-300); out = {re, im} */

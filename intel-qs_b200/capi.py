@@ -156,6 +156,8 @@ def load():
         "iqsb_mem_info": [c_vp, ctypes.POINTER(c_u64), ctypes.POINTER(c_u64)],
         "iqsb_set_stream": [c_vp, c_vp], "iqsb_get_stream": [c_vp], "iqsb_set_arith": [c_vp, c_int], "iqsb_get_arith": [c_vp],
         "iqsb_launch_count": [c_vp], "iqsb_nvlink_bytes": [c_vp],
+        "iqsb_prob_all": [c_vp, c_vp, c_int], "iqsb_pauli_expect": [c_vp, c_u64, c_u64, c_u64, c_u64, c_vp],
+        "iqsb_profile": [c_vp, c_int], "iqsb_profile_read": [c_vp, c_vp, ctypes.c_size_t],
         "iqsb_timer_start": [c_vp], "iqsb_timer_stop": [c_vp, ctypes.POINTER(c_dbl)],
         "iqsb_event_record": [c_vp, c_int], "iqsb_event_elapsed": [c_vp, c_int, c_int, ctypes.POINTER(c_dbl)],
         "iqsb_allreduce_f64": [c_vp, c_vp, c_int, c_int],
@@ -287,6 +289,21 @@ class Context:
     def nvlink_bytes(self):
         return int(self.L.iqsb_nvlink_bytes(self.h))
 
+    def profile(self, on):
+        """start (clearing) / stop the per-kernel-class device timing"""
+        _chk(self.L.iqsb_profile(self.h, int(bool(on))))
+
+    def profile_read(self):
+        """{class name: {"launches", "ms", "bytes"}} of the last profiled region"""
+        import json
+
+        buf = ctypes.create_string_buffer(1 << 16)
+        _chk(self.L.iqsb_profile_read(self.h, buf, len(buf)))
+        d = json.loads(buf.value.decode())
+        out = {c["name"]: {"launches": c["launches"], "ms": c["ms"], "bytes": c["bytes"]} for c in d["classes"]}
+        out["_overflow"] = d["overflow"]
+        return out
+
     def timer_start(self):
         _chk(self.L.iqsb_timer_start(self.h))
 
@@ -395,6 +412,19 @@ class State:
     def gate2(self, pos_high, pos_low, m16):
         mm = np.ascontiguousarray(np.asarray(m16, dtype=np.complex128).reshape(16)).view(np.float64)
         _chk(self.L.iqsb_gate2(self.h, pos_high, pos_low, mm.ctypes.data_as(c_vp)))
+
+    def prob_all(self):
+        """[sum |a|^2, P(bit 0 = 1), P(bit 1 = 1), ...] over the local shard, one read of the state"""
+        n = int(self.local_amps).bit_length() - 1
+        out = (ctypes.c_double * (n + 1))()
+        _chk(self.L.iqsb_prob_all(self.h, out, n + 1))
+        return np.array(out[:])
+
+    def pauli_expect(self, xmask, ymask, zmask, glb_start=0, with_norm=False):
+        """<psi| X^xmask Y^ymask Z^zmask |psi>, read-only (with_norm: also sum |a|^2 from the same read)"""
+        out = (ctypes.c_double * 2)()
+        _chk(self.L.iqsb_pauli_expect(self.h, c_u64(xmask), c_u64(ymask), c_u64(zmask), c_u64(glb_start), out))
+        return (out[0], out[1]) if with_norm else out[0]
 
     def fused(self, gates):
         """gates: list of (kind, control, target, m8)."""

@@ -7,6 +7,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <string>
+#include <vector>
+
 #include "iqsb_internal.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -18,13 +21,101 @@ void iqsb_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
-int iqsb_check_launch(iqsb_ctx *ctx, const char *what) {
+// Per-kernel-class timing: while profiling is on, every launch is followed by a CUDA event on the
+// engine's stream; the time between two consecutive events is the duration of the kernel between them
+// (the stream is kept busy by the caller, so there is no idle time to mis-attribute; what little
+// there is counts against the kernel, never for it).
+struct iqsb_prof {
+  bool on = false, overflow = false;
+  std::vector<cudaEvent_t> pool;  // pool[0] = start marker, pool[i + 1] closes recs[i]
+  struct Rec {
+    const char *name;
+    double bytes;
+  };
+  std::vector<Rec> recs;
+};
+static const size_t kMaxProfLaunches = 1u << 16;
+
+int iqsb_check_launch(iqsb_ctx *ctx, const char *what, double algo_bytes) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     iqsb_set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
     return IQSB_ERR_CUDA;
   }
   ctx->launches++;
+  iqsb_prof *p = ctx->prof;
+  if (p && p->on) {
+    if (p->recs.size() >= kMaxProfLaunches) {
+      p->overflow = true;
+    } else {
+      const size_t slot = p->recs.size() + 1;
+      if (p->pool.size() <= slot) {
+        cudaEvent_t ev;
+        IQSB_CUDA(cudaEventCreate(&ev));
+        p->pool.push_back(ev);
+      }
+      IQSB_CUDA(cudaEventRecord(p->pool[slot], ctx->stream));
+      p->recs.push_back({what, algo_bytes});
+    }
+  }
+  return IQSB_OK;
+}
+
+extern "C" int iqsb_profile(iqsb_ctx *ctx, int on) {
+  IQSB_REQUIRE(ctx, "iqsb_profile: null context");
+  if (!ctx->prof) ctx->prof = new iqsb_prof();
+  iqsb_prof *p = ctx->prof;
+  if (on) {
+    p->recs.clear();
+    p->overflow = false;
+    if (p->pool.empty()) {
+      cudaEvent_t ev;
+      IQSB_CUDA(cudaEventCreate(&ev));
+      p->pool.push_back(ev);
+    }
+    IQSB_CUDA(cudaEventRecord(p->pool[0], ctx->stream));
+  }
+  p->on = on != 0;
+  return IQSB_OK;
+}
+
+// JSON text: {"overflow": false, "classes": [{"name": "...", "launches": n, "ms": t, "bytes": b}, ...]}
+extern "C" int iqsb_profile_read(iqsb_ctx *ctx, char *out, size_t cap) {
+  IQSB_REQUIRE(ctx && out && cap > 0, "iqsb_profile_read: null argument");
+  out[0] = 0;
+  iqsb_prof *p = ctx->prof;
+  std::string js = "{\"overflow\": ";
+  js += (p && p->overflow) ? "true" : "false";
+  js += ", \"classes\": [";
+  if (p && !p->recs.empty()) {
+    IQSB_CUDA(cudaEventSynchronize(p->pool[p->recs.size()]));
+    struct Agg {
+      const char *name;
+      uint64_t n;
+      double ms, bytes;
+    };
+    std::vector<Agg> agg;
+    for (size_t i = 0; i < p->recs.size(); ++i) {
+      float ms = 0.f;
+      IQSB_CUDA(cudaEventElapsedTime(&ms, p->pool[i], p->pool[i + 1]));
+      size_t k = 0;
+      for (; k < agg.size(); ++k)
+        if (agg[k].name == p->recs[i].name || strcmp(agg[k].name, p->recs[i].name) == 0) break;
+      if (k == agg.size()) agg.push_back({p->recs[i].name, 0, 0., 0.});
+      agg[k].n++;
+      agg[k].ms += ms;
+      agg[k].bytes += p->recs[i].bytes;
+    }
+    char buf[256];
+    for (size_t k = 0; k < agg.size(); ++k) {
+      snprintf(buf, sizeof(buf), "%s{\"name\": \"%s\", \"launches\": %llu, \"ms\": %.6f, \"bytes\": %.1f}", k ? ", " : "", agg[k].name,
+               (unsigned long long)agg[k].n, agg[k].ms, agg[k].bytes);
+      js += buf;
+    }
+  }
+  js += "]}";
+  IQSB_REQUIRE(js.size() + 1 <= cap, "iqsb_profile_read: buffer of %zu bytes is too small (%zu needed)", cap, js.size() + 1);
+  memcpy(out, js.c_str(), js.size() + 1);
   return IQSB_OK;
 }
 
@@ -70,7 +161,13 @@ extern "C" int iqsb_init(int rank, int nranks, const void *uid, int device, iqsb
   if (const char *a = getenv("IQS_B200_ARITH")) ctx->arith = (strcmp(a, "fma") == 0 || strcmp(a, "FMA") == 0) ? IQSB_ARITH_FMA : IQSB_ARITH_EXACT;
   if (nranks > 1) {
     int rc = iqsb_comm_init(ctx, uid);
-    if (rc != IQSB_OK) return rc;
+    if (rc != IQSB_OK) {  // keep the message of the failure, release everything acquired so far
+      std::string why = g_err;
+      ctx->nranks = 1;  // nothing of the communication layer to tear down
+      iqsb_finalize(ctx);
+      iqsb_set_error("%s", why.c_str());
+      return rc;
+    }
   }
   *out = ctx;
   return IQSB_OK;
@@ -87,10 +184,15 @@ extern "C" int iqsb_finalize(iqsb_ctx *ctx) {
   cudaFreeHost(ctx->h_result);
   cudaFreeHost(ctx->stage_h);
   cudaFree(ctx->stage_d);
+  cudaFree(ctx->d_tile_counter);
   if (ctx->slots) {
     for (int i = 0; i < kMaxEventSlots; ++i)
       if (ctx->slots[i]) cudaEventDestroy(ctx->slots[i]);
     delete[] ctx->slots;
+  }
+  if (ctx->prof) {
+    for (cudaEvent_t ev : ctx->prof->pool) cudaEventDestroy(ev);
+    delete ctx->prof;
   }
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);

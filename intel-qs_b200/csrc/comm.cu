@@ -92,7 +92,7 @@ struct iqsb_peer_table {
 
 namespace {
 
-constexpr int kMaxCollDoubles = 32;
+constexpr int kMaxCollDoubles = 64;
 
 // Every rank stores `epoch` into slot `me` of every peer's flag array, then waits until all
 // of its own slots reached `epoch`.  Kernel boundaries on the stream order it after the

@@ -165,7 +165,8 @@ extern "C" int iqsb_exchange_bits(iqsb_state *st, unsigned M, int k, const unsig
       if (w1) k_exchange<Cx<float>><<<grid, kBlock, 0, ctx->stream>>>((Cx<float> *)st->d, g);
       else k_exchange<Chunk<float>><<<grid, kBlock, 0, ctx->stream>>>((Chunk<float> *)st->d, g);
     }
-    IQSB_TRY(iqsb_check_launch(ctx, "k_exchange"));
+    // "bytes" of this class = what the link carries per rank and direction (loads one way, stores the other)
+    IQSB_TRY(iqsb_check_launch(ctx, "k_exchange", (double)pl.link_amps * st->amp_bytes()));
   }
   ctx->nvlink_bytes += pl.link_amps * st->amp_bytes();
   return iqsb_peer_barrier(ctx);  // the partners' stores into this shard are complete

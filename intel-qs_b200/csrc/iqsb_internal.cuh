@@ -45,6 +45,7 @@ void iqsb_set_error(const char *fmt, ...);
 // host-side objects behind the opaque handles
 // ---------------------------------------------------------------------------------------
 struct iqsb_peer_table;  // comm.cu
+struct iqsb_prof;        // api.cu: per-kernel-class device timing (iqsb_profile)
 
 struct iqsb_ctx {
   int rank = 0, nranks = 1, device = 0, num_sms = 148;
@@ -66,6 +67,8 @@ struct iqsb_ctx {
   unsigned char *stage_h = nullptr, *stage_d = nullptr;
   size_t stage_off = 0;
   int arith = IQSB_ARITH_EXACT;  // iqsb_set_arith
+  iqsb_prof *prof = nullptr;     // iqsb_profile
+  unsigned long long *d_tile_counter = nullptr;  // tile scheduler of the fused kernel
 };
 constexpr size_t kStageBytes = 1u << 20;
 
@@ -82,7 +85,7 @@ struct iqsb_state {
 };
 
 constexpr int kMaxRedBlocks = 148 * 8;
-constexpr int kMaxRedOut = 12;
+constexpr int kMaxRedOut = 40;
 constexpr int kMaxEventSlots = 4096;
 
 // ---------------------------------------------------------------------------------------
@@ -250,7 +253,9 @@ static inline Mat2<T> make_mat(const double m[8]) {
   return r;
 }
 
-int iqsb_check_launch(iqsb_ctx *ctx, const char *what);
+// after every kernel launch: error check, launch count and (when profiling) a CUDA event on the stream.
+// `what` must be a string literal; `algo_bytes` = algorithmic bytes of the launch (0: not stated)
+int iqsb_check_launch(iqsb_ctx *ctx, const char *what, double algo_bytes = 0.0);
 
 // kernels_gate.cu
 int iqsb_launch_pairs(iqsb_state *st, void *s0, void *s1, int width, const Geom &g, const double m[8]);

@@ -51,11 +51,20 @@ namespace {
 #ifndef IQSB_FUSED_TILE
 #define IQSB_FUSED_TILE 12
 #endif
+#ifndef IQSB_FUSED_REGBITS
+#define IQSB_FUSED_REGBITS 3
+#endif
 constexpr int kThreads = 256;
 constexpr int kMaxFusedGates = 4096;
 constexpr int kTile = IQSB_FUSED_TILE;  // tile exponent (<= 12)
+// (A variant with two tile buffers of 2^11 amplitudes per CTA, the next tile fetched while the current
+// one is worked on, was measured and dropped -- profiles/r02f_fused_variants.log: 68.7 vs 61.2 ms per
+// bench layer on the same box.  With 3 CTAs per SM the loads of one CTA already overlap the
+// arithmetic of the others; the kernel is bound by instruction issue inside the tile.)
 constexpr int kLow = 4;                 // lowest positions always in the tile
-constexpr int kRegBits = 3;             // tile bits held in registers by a group
+constexpr int kRegBits = IQSB_FUSED_REGBITS;  // tile bits held in registers by a group (3 or 4)
+constexpr int kAmps = 1 << kRegBits;          // amplitudes per thread
+static_assert(kRegBits == 3 || kRegBits == 4, "register blocking");
 constexpr int kBatchGates = 48;         // descriptors resident in shared memory at a time
 constexpr int kBatchGroups = 24;
 constexpr int kReorderWindow = 512;     // how far the planner looks past the first skipped gate
@@ -70,18 +79,19 @@ struct alignas(16) FGate {
   uint8_t tbit;   // register bit of the target (0..2)
   uint8_t ckind;  // 0 none | 1 register bit (pairs enabled: `en`) | 2 thread bit `c` | 3 bit `c` of the tile's base index
   uint8_t c;
-  uint8_t en;     // 4-bit mask of the register pairs the gate acts on
-  uint8_t pad8[3];
+  uint8_t en;     // mask of the kAmps/2 register pairs the gate acts on
+  uint8_t last;   // 1: last gate of its group
+  uint8_t pad8[2];
   uint32_t pad32[2];
 };
 
 struct alignas(16) GroupDesc {
   uint16_t lo[32];  // swizzled slot contributed by thread bits 0..4
   uint16_t hi[16];  // ... by thread bits 5..8
-  uint16_t p[3];    // swizzled slot offset of register bit k
+  uint16_t p[4];    // swizzled slot offset of register bit k
   uint16_t gate_first, gate_count;
-  uint16_t log2_threads;  // tile exponent - 3
-  uint16_t pad[2];
+  uint16_t log2_threads;  // tile exponent - kRegBits
+  uint16_t pad;
 };
 static_assert(sizeof(GroupDesc) == 112, "group descriptor layout");
 
@@ -123,7 +133,10 @@ __device__ __forceinline__ void tile_load_async(Cx<T> *tile, const Chunk<T> *g, 
     cp_async_amp(tile + (s ^ 1u), src + 1);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 // tile -> global, U 32-byte stores in flight per thread; nchunks is a multiple of kThreads * U
 template <typename T, int U>
@@ -149,32 +162,38 @@ __device__ __forceinline__ void tile_store(const Cx<T> *tile, Chunk<T> *g, const
 // B = register bit of the target; pair k (k = 0..3) is (a[r0], a[r0 | 1 << B]) with r0 = k with a
 // zero inserted at bit B.  `en` selects the pairs (control on another register bit).
 template <typename T, int B, typename F>
-__device__ __forceinline__ void for_pairs(unsigned en, Cx<T> (&a)[8], F f) {
+__device__ __forceinline__ void for_pairs(Cx<T> (&a)[kAmps], F f) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < kAmps / 2; ++k) {
     const int r0 = ((k >> B) << (B + 1)) | (k & ((1 << B) - 1));
-    if (en & (1u << k)) f(a[r0], a[r0 | (1 << B)]);
+    f(a[r0], a[r0 | (1 << B)]);
   }
 }
 
 template <typename T, bool FMA, int B>
-__device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Mat2<T> &m, Cx<T> (&a)[8]) {
+__device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Mat2<T> &m, Cx<T> (&a)[kAmps]) {
   switch (cls) {
-    case kXExact:  // out0 = in1, out1 = in0
-      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
-        Cx<T> t = x;
-        x = y;
-        y = t;
-      });
+    case kXExact:  // out0 = in1, out1 = in0.  The only class that takes a control among the register bits
+                   // (`en` = the pairs whose control bit is set): CNOTs are moves between registers.
+#pragma unroll
+      for (int k = 0; k < kAmps / 2; ++k) {
+        const int r0 = ((k >> B) << (B + 1)) | (k & ((1 << B) - 1));
+        const bool on = (en >> k) & 1u;
+        const Cx<T> x = a[r0], y = a[r0 | (1 << B)];
+        a[r0].re = on ? y.re : x.re;
+        a[r0].im = on ? y.im : x.im;
+        a[r0 | (1 << B)].re = on ? x.re : y.re;
+        a[r0 | (1 << B)].im = on ? x.im : y.im;
+      }
       break;
     case kDiag1: {  // out0 = in0, out1 = m11 * in1
       const Cx<T> d = m.m11;
-      for_pairs<T, B>(en, a, [&](Cx<T> &, Cx<T> &y) { y = cmul(d, y); });
+      for_pairs<T, B>(a, [&](Cx<T> &, Cx<T> &y) { y = cmul(d, y); });
       break;
     }
     case kDiag: {
       const Cx<T> d0 = m.m00, d1 = m.m11;
-      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+      for_pairs<T, B>(a, [&](Cx<T> &x, Cx<T> &y) {
         x = cmul(d0, x);
         y = cmul(d1, y);
       });
@@ -182,7 +201,7 @@ __device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Ma
     }
     case kAnti: {
       const Cx<T> u = m.m01, l = m.m10;
-      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+      for_pairs<T, B>(a, [&](Cx<T> &x, Cx<T> &y) {
         const Cx<T> t = cmul(u, y);
         y = cmul(l, x);
         x = t;
@@ -191,7 +210,7 @@ __device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Ma
     }
     case kReal: {  // every imaginary part of the matrix is an exact zero (H, RY)
       const T r00 = m.m00.re, r01 = m.m01.re, r10 = m.m10.re, r11 = m.m11.re;
-      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+      for_pairs<T, B>(a, [&](Cx<T> &x, Cx<T> &y) {
         Cx<T> o0, o1;
         if (FMA) {
           o0.re = fma_c(r00, x.re, r01 * y.re);
@@ -211,7 +230,7 @@ __device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Ma
     }
     case kRealDiagImagOff: {  // m00, m11 real; m01, m10 imaginary (RX)
       const T r00 = m.m00.re, i01 = m.m01.im, i10 = m.m10.im, r11 = m.m11.re;
-      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+      for_pairs<T, B>(a, [&](Cx<T> &x, Cx<T> &y) {
         Cx<T> o0, o1;
         if (FMA) {
           o0.re = fma_c(r00, x.re, -(i01 * y.im));
@@ -230,7 +249,7 @@ __device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Ma
       break;
     }
     default:
-      for_pairs<T, B>(en, a, [&](Cx<T> &x, Cx<T> &y) {
+      for_pairs<T, B>(a, [&](Cx<T> &x, Cx<T> &y) {
         if (FMA) apply2x2_fma(m, x, y);
         else apply2x2(m, x, y);
       });
@@ -240,7 +259,8 @@ __device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Ma
 
 template <typename T, bool FMA>
 __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
-    k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, const unsigned char *__restrict__ desc, int nbatches) {
+    k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, const unsigned char *__restrict__ desc, int nbatches,
+            unsigned long long *__restrict__ next_tile) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cx<T> *tile = reinterpret_cast<Cx<T> *>(smem_raw);
   // chunk offset of tile-local chunk index c = lo | hi << 8 (c = tile-local amplitude index / 2)
@@ -249,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
   __shared__ __align__(16) FGate<T> s_gate[kBatchGates];
   __shared__ int s_pos[16];
   __shared__ int s_hdr[4];
+  __shared__ unsigned long long s_tile;
   const int nS = td.nS;  // pos[0] == 0 always
   if (threadIdx.x < kTile) s_pos[threadIdx.x] = td.pos[threadIdx.x];
   __syncthreads();
@@ -278,12 +299,25 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
   if (nbatches == 1) stage(0);
   __syncthreads();
   const unsigned nchunks = 1u << (nS - 1);
-  for (uint64_t o = blockIdx.x; o < nouter; o += gridDim.x) {
-    uint64_t base = o;  // amplitude index with zeros at the tile positions
+  // Tiles are handed out in address order from a global counter (next_tile != nullptr): the CTAs of
+  // the whole GPU then work inside one moving window of the state, whatever their individual pace.
+  // Thread 0 publishes the tile's base index (amplitude index with zeros at the tile positions) in
+  // shared memory; nothing 64-bit has to stay in registers across the arithmetic.
+  for (unsigned it = 0;; ++it) {
+    if (threadIdx.x == 0) {
+      uint64_t o = next_tile != nullptr ? atomicAdd(next_tile, 1ull) : (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
+      uint64_t base = ~0ull;
+      if (o < nouter) {
+        base = o;
 #pragma unroll 1
-    for (int k = 0; k < nS; ++k) base = insert_zero(base, (unsigned)s_pos[k]);
-    Chunk<T> *g = state + (base >> 1);
-    tile_load_async<T>(tile, g, g_lo, g_hi, nchunks);
+        for (int k = 0; k < nS; ++k) base = insert_zero(base, (unsigned)s_pos[k]);
+      }
+      s_tile = base;
+    }
+    __syncthreads();
+    if (s_tile == ~0ull) break;
+    tile_load_async<T>(tile, state + (s_tile >> 1), g_lo, g_hi, nchunks);
+    cp_async_wait<0>();
     for (int b = 0; b < nbatches; ++b) {
       if (nbatches > 1) {
         if (b) __syncthreads();  // nobody still reads the previous batch
@@ -292,32 +326,57 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
       __syncthreads();  // the tile is loaded, the descriptors are visible
       const int ngroups = s_hdr[0];
       for (int gi = 0; gi < ngroups; ++gi) {
-        const GroupDesc &G = s_group[gi];
-        const unsigned P0 = G.p[0], P1 = G.p[1], P2 = G.p[2];
-        const unsigned nthr = 1u << G.log2_threads;
-        const int gfirst = G.gate_first, glast = gfirst + G.gate_count;
-#pragma unroll 1
-        for (unsigned t = threadIdx.x; t < nthr; t += kThreads) {
-          const unsigned px = (unsigned)G.lo[t & 31u] ^ (unsigned)G.hi[t >> 5];
-          Cx<T> a[8];
+        // The group's addressing (a few 16-bit table entries) is read again for the write-back instead
+        // of being kept in registers across the gates -- the volatile reads stop the compiler from
+        // carrying (and spilling) ~17 registers of addresses through the arithmetic.
+        const volatile GroupDesc *G = &s_group[gi];
+        auto slots = [&](unsigned t, unsigned (&sl)[kAmps]) {
+          const unsigned px = (unsigned)G->lo[t & 31u] ^ (unsigned)G->hi[t >> 5];
+          unsigned P[kRegBits];
 #pragma unroll
-          for (int r = 0; r < 8; ++r) a[r] = tile[px ^ ((r & 1) ? P0 : 0u) ^ ((r & 2) ? P1 : 0u) ^ ((r & 4) ? P2 : 0u)];
+          for (int j = 0; j < kRegBits; ++j) P[j] = G->p[j];
+#pragma unroll
+          for (int r = 0; r < kAmps; ++r) {
+            unsigned sidx = px;
+#pragma unroll
+            for (int j = 0; j < kRegBits; ++j)
+              if (r & (1 << j)) sidx ^= P[j];
+            sl[r] = sidx;
+          }
+        };
 #pragma unroll 1
-          for (int gj = gfirst; gj < glast; ++gj) {
+        for (unsigned t = threadIdx.x; t < (1u << G->log2_threads); t += kThreads) {
+          Cx<T> a[kAmps];
+          {
+            unsigned sl[kAmps];
+            slots(t, sl);
+#pragma unroll
+            for (int r = 0; r < kAmps; ++r) a[r] = tile[sl[r]];
+          }
+          bool more = true;
+#pragma unroll 1
+          for (int gj = G->gate_first; more; ++gj) {
             const FGate<T> &fg = s_gate[gj];
             const unsigned cls = fg.cls, tbit = fg.tbit, ckind = fg.ckind, c = fg.c, en = fg.en;
-            if (ckind == 3 && !((base >> c) & 1ull)) continue;  // uniform over the CTA
+            more = fg.last == 0;
+            if (ckind == 3 && !((s_tile >> c) & 1ull)) continue;  // uniform over the CTA
             if (ckind == 2 && !((t >> c) & 1u)) continue;       // uniform over the warp when c >= 5 (the planner's choice)
             if (tbit == 0) apply_on_bit<T, FMA, 0>(cls, en, fg.m, a);
             else if (tbit == 1) apply_on_bit<T, FMA, 1>(cls, en, fg.m, a);
-            else apply_on_bit<T, FMA, 2>(cls, en, fg.m, a);
+            else if (kRegBits == 3 || tbit == 2) apply_on_bit<T, FMA, 2>(cls, en, fg.m, a);
+            else apply_on_bit<T, FMA, kRegBits - 1>(cls, en, fg.m, a);
           }
+          {
+            unsigned sl[kAmps];
+            slots(t, sl);
 #pragma unroll
-          for (int r = 0; r < 8; ++r) tile[px ^ ((r & 1) ? P0 : 0u) ^ ((r & 2) ? P1 : 0u) ^ ((r & 4) ? P2 : 0u)] = a[r];
+            for (int r = 0; r < kAmps; ++r) tile[sl[r]] = a[r];
+          }
         }
         __syncthreads();
       }
     }
+    Chunk<T> *g = state + (s_tile >> 1);
     if (nchunks % (kThreads * 2) == 0) tile_store<T, 2>(tile, g, g_lo, g_hi, nchunks);
     else tile_store<T, 1>(tile, g, g_lo, g_hi, nchunks);
     __syncthreads();
@@ -344,34 +403,68 @@ struct HostGroup {
   std::vector<int> gates;  // indices into the run's gate list
   int rs[kRegBits];        // register slots (tile-local bits)
   int nrs = 0;
+  uint64_t qmask = 0;  // positions (targets and controls) its gates touch
+  unsigned arith_ctrl = 0;  // tile slots that control an ARITHMETIC gate of the group: never register bits
+  bool has(int slot) const {
+    for (int j = 0; j < nrs; ++j)
+      if (rs[j] == slot) return true;
+    return false;
+  }
 };
 
 // Build the batches (header + groups + gates) of one run.  `run` lists indices into `in`, in
 // execution order; every target is in the tile.
 template <typename T>
-void build_batches(const iqsb_fgate *in, const std::vector<int> &run, const TileDesc &td, std::vector<unsigned char> &out, int &nbatches) {
+void build_batches(const iqsb_fgate *in, const std::vector<int> &run, const TileDesc &td, bool reorder, std::vector<unsigned char> &out, int &nbatches) {
   const int nS = td.nS;
   int slot_of[64];
   for (int p = 0; p < 64; ++p) slot_of[p] = -1;
   for (int k = 0; k < nS; ++k) slot_of[td.pos[k]] = k;
-  // 1. groups: consecutive gates on at most kRegBits distinct target slots
+  // 1. groups: gates on at most kRegBits distinct target slots.  Arithmetic gates join the last
+  //    group (or open a new one); an exact X / CNOT commutes without rounding with gates on other
+  //    qubits, so it may join the EARLIEST group after the last gate it shares a qubit with.
   std::vector<HostGroup> groups;
-  HostGroup cur;
-  auto close = [&]() {
-    if (!cur.gates.empty()) groups.push_back(cur);
-    cur = HostGroup();
-  };
   for (size_t k = 0; k < run.size(); ++k) {
-    const int ts = slot_of[in[run[k]].target];
-    bool have = false;
-    for (int j = 0; j < cur.nrs; ++j) have = have || cur.rs[j] == ts;
-    if ((!have && cur.nrs == kRegBits) || (int)cur.gates.size() == kBatchGates) close();
-    have = false;
-    for (int j = 0; j < cur.nrs; ++j) have = have || cur.rs[j] == ts;
-    if (!have) cur.rs[cur.nrs++] = ts;
-    cur.gates.push_back((int)k);
+    const iqsb_fgate &q = in[run[k]];
+    const int ts = slot_of[q.target];
+    const uint64_t qm = (1ull << (unsigned)q.target) | (q.kind == 1 ? 1ull << (unsigned)q.control : 0ull);
+    // Only exact X takes a control among the register bits (there it is a move between registers);
+    // the control of an arithmetic gate must be a thread bit, so that the arithmetic classes stay
+    // straight-line code over all register pairs.
+    const bool perm = is_xexact(q.m);
+    const int cs = q.kind == 1 ? slot_of[q.control] : -1;
+    const bool arith_ctrl = !perm && cs >= 0;
+    auto room = [&](const HostGroup &g) {
+      if (!(g.has(ts) || g.nrs < kRegBits) || (int)g.gates.size() >= kBatchGates) return false;
+      if (!g.has(ts) && ((g.arith_ctrl >> ts) & 1u)) return false;  // ts would become a register bit
+      if (arith_ctrl) {
+        if (g.has(cs)) return false;
+        // enough other slots must remain to fill the register bits
+        const unsigned ac = g.arith_ctrl | (1u << cs);
+        if (__builtin_popcount(ac) + kRegBits > nS) return false;
+      }
+      return true;
+    };
+    int where = -1;
+    if (reorder && perm && !groups.empty()) {
+      int e = 0;
+      for (int j = (int)groups.size() - 1; j >= 0; --j)
+        if (groups[j].qmask & qm) { e = j; break; }
+      for (int j = e; j < (int)groups.size() && where < 0; ++j)
+        if (room(groups[j])) where = j;
+    } else if (!groups.empty() && room(groups.back())) {
+      where = (int)groups.size() - 1;
+    }
+    if (where < 0) {
+      groups.push_back(HostGroup());
+      where = (int)groups.size() - 1;
+    }
+    HostGroup &g = groups[where];
+    if (!g.has(ts)) g.rs[g.nrs++] = ts;
+    g.gates.push_back((int)k);
+    g.qmask |= qm;
+    if (arith_ctrl) g.arith_ctrl |= 1u << cs;
   }
-  close();
   // 2. descriptors
   out.clear();
   nbatches = 0;
@@ -401,11 +494,12 @@ void build_batches(const iqsb_fgate *in, const std::vector<int> &run, const Tile
       const iqsb_fgate &q = in[run[k]];
       if (q.kind == 1 && slot_of[q.control] >= 0) is_ctrl[slot_of[q.control]] = true;
     }
-    // spare register bits: controls first (the gate then acts on whole register pairs), then any slot
+    // spare register bits: controls of X gates first (a CNOT is then a move between registers), then
+    // any slot that does not control an arithmetic gate
     for (int s = 0; s < nS && hg.nrs < kRegBits; ++s)
-      if (is_ctrl[s] && !used[s]) { hg.rs[hg.nrs++] = s; used[s] = true; }
+      if (is_ctrl[s] && !used[s] && !((hg.arith_ctrl >> s) & 1u)) { hg.rs[hg.nrs++] = s; used[s] = true; }
     for (int s = nS - 1; s >= 0 && hg.nrs < kRegBits; --s)
-      if (!used[s]) { hg.rs[hg.nrs++] = s; used[s] = true; }
+      if (!used[s] && !((hg.arith_ctrl >> s) & 1u)) { hg.rs[hg.nrs++] = s; used[s] = true; }
     // thread bits -> tile slots.  Bits 0..2 (the lanes of a quarter-warp): three slots with distinct
     // residues mod 3, preferably not controls; controls go to the highest thread bits (warp-uniform).
     int dep[16], ndep = 0;
@@ -453,7 +547,7 @@ void build_batches(const iqsb_fgate *in, const std::vector<int> &run, const Tile
       const int ts = slot_of[q.target];
       for (int j = 0; j < kRegBits; ++j)
         if (hg.rs[j] == ts) o.tbit = (uint8_t)j;
-      o.en = 0xF;
+      o.en = (uint8_t)((1u << (kAmps / 2)) - 1u);
       if (q.kind == 1) {
         const int cs = slot_of[q.control];
         if (cs < 0) { o.ckind = 3; o.c = (uint8_t)q.control; }
@@ -465,7 +559,7 @@ void build_batches(const iqsb_fgate *in, const std::vector<int> &run, const Tile
           o.ckind = 1;
           o.c = (uint8_t)cb;
           o.en = 0;
-          for (int kk = 0; kk < 4; ++kk) {
+          for (int kk = 0; kk < kAmps / 2; ++kk) {
             const int r0 = ((kk >> o.tbit) << (o.tbit + 1)) | (kk & ((1 << o.tbit) - 1));
             if ((r0 >> cb) & 1) o.en |= (uint8_t)(1u << kk);
           }
@@ -473,17 +567,20 @@ void build_batches(const iqsb_fgate *in, const std::vector<int> &run, const Tile
       }
       bgates.push_back(o);
     }
+    bgates.back().last = 1;
   }
   flush();
 }
 
+bool dynamic_tiles();
+
 // one run: the gates `run` (indices into `in`, execution order) all have their target in the tile `td`
 template <typename T>
-int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run, const TileDesc &td) {
+int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run, const TileDesc &td, bool reorder) {
   iqsb_ctx *ctx = st->ctx;
   std::vector<unsigned char> blob;
   int nbatches = 0;
-  build_batches<T>(in, run, td, blob, nbatches);
+  build_batches<T>(in, run, td, reorder, blob, nbatches);
   if (nbatches == 0) return IQSB_OK;
   // descriptors travel through the context's staging ring: written into pinned memory, copied in
   // stream order; the host only waits when the ring wraps around
@@ -511,8 +608,14 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run
   uint64_t nouter = st->local_amps >> td.nS;
   uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
   unsigned grid = (unsigned)(nouter < cap ? nouter : cap);
-  kernel<<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, nbatches);
-  return iqsb_check_launch(ctx, "k_fused");
+  unsigned long long *counter = nullptr;
+  if (dynamic_tiles()) {
+    if (!ctx->d_tile_counter) IQSB_CUDA(cudaMalloc((void **)&ctx->d_tile_counter, sizeof(unsigned long long)));
+    counter = ctx->d_tile_counter;
+    IQSB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+  }
+  kernel<<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, nbatches, counter);
+  return iqsb_check_launch(ctx, "k_fused", 2.0 * (double)st->local_amps * st->amp_bytes());
 }
 
 // The planner.  order = gate indices in execution order, run_end[r] = one past the last entry of
@@ -575,6 +678,11 @@ int plan_runs(const iqsb_fgate *gates, int ngates, unsigned log2_local, bool reo
   return IQSB_OK;
 }
 
+bool dynamic_tiles() {  // IQS_B200_FUSED_DYNAMIC=0: static round-robin of tiles over CTAs
+  const char *e = getenv("IQS_B200_FUSED_DYNAMIC");
+  return !(e && *e == '0');
+}
+
 bool reorder_default() {
   static int v = -1;
   if (v < 0) {
@@ -633,14 +741,15 @@ extern "C" int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates) {
   std::vector<int> order((size_t)ngates), run_end((size_t)ngates);
   std::vector<uint8_t> tiles((size_t)ngates * 16);
   int nruns = 0;
-  IQSB_TRY(plan_runs(gates, ngates, st->log2_local, reorder_default(), order.data(), run_end.data(), tiles.data(), ngates, &nruns));
+  const bool reorder = reorder_default();
+  IQSB_TRY(plan_runs(gates, ngates, st->log2_local, reorder, order.data(), run_end.data(), tiles.data(), ngates, &nruns));
   int first = 0;
   for (int r = 0; r < nruns; ++r) {
     TileDesc td;
     td.nS = tiles[r * 16];
     for (int k = 0; k < kTile; ++k) td.pos[k] = tiles[r * 16 + 1 + k];
     std::vector<int> run(order.begin() + first, order.begin() + run_end[r]);
-    int rc = st->dtype == IQSB_F64 ? launch_run<double>(st, gates, run, td) : launch_run<float>(st, gates, run, td);
+    int rc = st->dtype == IQSB_F64 ? launch_run<double>(st, gates, run, td, reorder) : launch_run<float>(st, gates, run, td, reorder);
     if (rc != IQSB_OK) return rc;
     first = run_end[r];
   }

@@ -353,7 +353,7 @@ int iqsb_launch_pairs(iqsb_state *st, void *s0, void *s1, int width, const Geom 
       if (width == 2) k_move_w2<float><<<grid, kBlock, 0, ctx->stream>>>((Chunk<float> *)s0, (Chunk<float> *)s1, g);
       else k_move_w1<float><<<grid, kBlock, 0, ctx->stream>>>((Cx<float> *)s0, (Cx<float> *)s1, g);
     }
-    return iqsb_check_launch(ctx, "k_move");
+    return iqsb_check_launch(ctx, s0 != s1 ? "k_move_peer" : "k_move", (double)g.nwork * 4.0 * width * st->amp_bytes());
   }
   if (st->dtype == IQSB_F64) {
     if (width == 2)
@@ -370,7 +370,9 @@ int iqsb_launch_pairs(iqsb_state *st, void *s0, void *s1, int width, const Geom 
       k_pairs_w1<float><<<grid, kBlock, 0, ctx->stream>>>((Cx<float> *)s0, (Cx<float> *)s1, g,
                                                          make_mat<float>(m));
   }
-  return iqsb_check_launch(ctx, "k_pairs");
+  // one work item = two partners of `width` amplitudes, read and written
+  const char *what = s0 != s1 ? "k_pairs_peer" : (g.ins1 == 63u ? "k_pairs_dense1" : "k_pairs_ctrl");
+  return iqsb_check_launch(ctx, what, (double)g.nwork * 4.0 * width * st->amp_bytes());
 }
 
 int iqsb_launch_inchunk(iqsb_state *st, void *s, const Geom &g, const double m[8]) {
@@ -381,7 +383,7 @@ int iqsb_launch_inchunk(iqsb_state *st, void *s, const Geom &g, const double m[8
     k_inchunk<double><<<grid, kBlock, 0, ctx->stream>>>((Chunk<double> *)s, g, make_mat<double>(m));
   else
     k_inchunk<float><<<grid, kBlock, 0, ctx->stream>>>((Chunk<float> *)s, g, make_mat<float>(m));
-  return iqsb_check_launch(ctx, "k_inchunk");
+  return iqsb_check_launch(ctx, "k_inchunk", (double)g.nwork * 4.0 * st->amp_bytes());
 }
 
 int iqsb_launch_scale_subset(iqsb_state *st, void *s, int width, const Geom &g, const double f[2]) {

@@ -225,6 +225,107 @@ __global__ void __launch_bounds__(kBlock) k_entropy(const Cx<T> *__restrict__ s,
   block_reduce_store<11, false>(acc, partials);
 }
 
+// All marginals in one sweep (16 B per amplitude read once): out[0] = sum |a|^2, out[1 + q] = sum of
+// |a_i|^2 over the local indices i with bit q set.  The grid has a power-of-two number of threads,
+// thread t visits chunks t, t + 2^S, t + 2 * 2^S, ...: the low S chunk bits are the thread's own
+// (credited once, at the end, from its total), bit 0 of the amplitude index is the position inside the
+// chunk, and only the few bits above S cost a predicated add per chunk.
+constexpr int kProbOut = 40;   // 1 + up to 39 local positions
+constexpr int kProbHigh = 16;  // positions above the thread-index bits
+constexpr int kProbLog2Threads = 18;  // full grid: 2^18 threads = 1024 blocks, all resident
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+    k_prob_all(const Chunk<T> *__restrict__ s, uint64_t nchunks, unsigned log2_threads, unsigned nbits, double *partials) {
+  const uint64_t t = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+  const uint64_t stride = 1ull << log2_threads;
+  double total = 0.0, odd = 0.0, hi[kProbHigh];
+#pragma unroll
+  for (int j = 0; j < kProbHigh; ++j) hi[j] = 0.0;
+  auto add = [&](uint64_t k, const Chunk<T> &v) {
+    const double na = norm_d(v.a), nb = norm_d(v.b), p = na + nb;
+    total += p;
+    odd += nb;
+#pragma unroll
+    for (int j = 0; j < kProbHigh; ++j)
+      if ((k >> j) & 1ull) hi[j] += p;
+  };
+  if (t < nchunks) {
+    const uint64_t niter = nchunks >> log2_threads;
+    uint64_t k = 0;
+    for (; k + 3 < niter; k += 4) {
+      Chunk<T> v0 = ld_chunk(s + t + k * stride), v1 = ld_chunk(s + t + (k + 1) * stride);
+      Chunk<T> v2 = ld_chunk(s + t + (k + 2) * stride), v3 = ld_chunk(s + t + (k + 3) * stride);
+      add(k, v0); add(k + 1, v1); add(k + 2, v2); add(k + 3, v3);
+    }
+    for (; k < niter; ++k) add(k, ld_chunk(s + t + k * stride));
+  }
+  double acc[kProbOut];
+#pragma unroll
+  for (int q = 0; q < kProbOut; ++q) acc[q] = 0.0;
+  acc[0] = total;
+  acc[1] = odd;
+#pragma unroll
+  for (int q = 1; q < kProbOut - 1; ++q) {  // amplitude bit q = chunk bit q - 1
+    const unsigned cb = (unsigned)q - 1u;
+    double v = 0.0;
+    if ((unsigned)q < nbits) {
+      // bits above the thread index exist only with the full grid (log2_threads == kProbLog2Threads)
+      if (cb < log2_threads) v = ((t >> cb) & 1ull) ? total : 0.0;
+      else if (cb >= (unsigned)kProbLog2Threads && cb - kProbLog2Threads < (unsigned)kProbHigh) v = hi[cb >= (unsigned)kProbLog2Threads ? cb - kProbLog2Threads : 0];
+    }
+    acc[1 + q] = v;
+  }
+  block_reduce_store<kProbOut, false>(acc, partials);
+}
+
+// Read-only expectation value of a Pauli string (X on the bits of xmask, Y on ymask, Z on zmask):
+// P|i> = i^ny (-1)^popc(i & (y|z)) |i ^ f>, f = x | y, so <psi|P|psi> = i^ny * S with
+// S = sum_i s_i psi_i conj(psi_{i^f}).  The pair (i, i^f) contributes s_i (w + (-1)^ny conj(w)),
+// w = psi_i conj(psi_{i^f}); the kernel visits every pair once (16 B per amplitude, nothing written)
+// and accumulates sum s_i Re w and sum s_i Im w.  Work item = chunk c with the highest flip bit clear,
+// partner chunk c ^ (f >> 1), its two amplitudes swapped when f has bit 0.
+template <typename T, bool INCHUNK>
+__global__ void __launch_bounds__(kBlock)
+    k_pauli(const Chunk<T> *__restrict__ s, uint64_t nwork, unsigned hb, uint64_t fchunk, int swap, uint64_t smask, uint64_t glb_start, double *partials) {
+  double acc[3] = {0.0, 0.0, 0.0};  // sum s Re w, sum s Im w, sum |psi|^2 (every amplitude is read exactly once)
+  const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+  auto pair = [&](uint64_t i, Cx<T> a, Cx<T> b) {  // w = a conj(b), sign from the global index of a
+    const double ar = (double)a.re, ai = (double)a.im, br = (double)b.re, bi = (double)b.im;
+    const double wr = ar * br + ai * bi, wi = ai * br - ar * bi;
+    const bool neg = __popcll((glb_start + i) & smask) & 1;
+    acc[0] += neg ? -wr : wr;
+    acc[1] += neg ? -wi : wi;
+    acc[2] += (ar * ar + ai * ai) + (br * br + bi * bi);
+  };
+  auto one = [&](uint64_t t2, const Chunk<T> &A, const Chunk<T> &B) {
+    const uint64_t c = INCHUNK ? t2 : insert_zero(t2, hb);
+    if (INCHUNK) {
+      pair(2 * c, A.a, A.b);
+    } else {
+      pair(2 * c, A.a, swap ? B.b : B.a);
+      pair(2 * c + 1, A.b, swap ? B.a : B.b);
+    }
+  };
+  uint64_t t = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+  for (; t + stride < nwork; t += 2 * stride) {
+    const uint64_t c0 = INCHUNK ? t : insert_zero(t, hb), c1 = INCHUNK ? t + stride : insert_zero(t + stride, hb);
+    Chunk<T> A0 = ld_chunk(s + c0), A1 = ld_chunk(s + c1), B0 = A0, B1 = A1;
+    if (!INCHUNK) {
+      B0 = ld_chunk(s + (c0 ^ fchunk));
+      B1 = ld_chunk(s + (c1 ^ fchunk));
+    }
+    one(t, A0, B0);
+    one(t + stride, A1, B1);
+  }
+  for (; t < nwork; t += stride) {
+    const uint64_t c0 = INCHUNK ? t : insert_zero(t, hb);
+    Chunk<T> A0 = ld_chunk(s + c0), B0 = A0;
+    if (!INCHUNK) B0 = ld_chunk(s + (c0 ^ fchunk));
+    one(t, A0, B0);
+  }
+  block_reduce_store<3, false>(acc, partials);
+}
+
 inline int red_grid(const iqsb_ctx *ctx, uint64_t nwork) {
   uint64_t want = (nwork + kBlock - 1) / kBlock;
   int cap = ctx->num_sms * 8;
@@ -303,6 +404,76 @@ extern "C" int iqsb_parity_expect(iqsb_state *st, uint64_t mask, uint64_t glb_st
     k_parity<float><<<grid, kBlock, 0, ctx->stream>>>((const Chunk<float> *)st->d, nchunks, mask, glb_start, ctx->d_partials);
   IQSB_TRY(iqsb_check_launch(ctx, "k_parity"));
   return finish<1, false>(ctx, grid, out);
+}
+
+extern "C" int iqsb_prob_all(iqsb_state *st, double *out, int nout) {
+  IQSB_REQUIRE(st && out, "iqsb_prob_all: null argument");
+  const unsigned M = st->log2_local;
+  IQSB_REQUIRE(nout >= (int)M + 1, "iqsb_prob_all: out[] must hold 1 + log2(local_amps) = %u doubles", M + 1);
+  IQSB_REQUIRE(M >= 1 && M + 1 <= (unsigned)kProbOut - 1, "iqsb_prob_all: shard of 2^%u amplitudes is not supported", M);
+  iqsb_ctx *ctx = st->ctx;
+  const uint64_t nchunks = st->local_amps / 2;
+  // a power-of-two number of threads, at most 1024 blocks (all resident: 148 SMs x 8)
+  unsigned log2_threads = kProbLog2Threads;
+  if (M - 1 < log2_threads) log2_threads = M - 1;
+  IQSB_REQUIRE(M - 1 - log2_threads <= (unsigned)kProbHigh, "iqsb_prob_all: shard too large");
+  const uint64_t nthreads = 1ull << log2_threads;
+  const int grid = (int)((nthreads + kBlock - 1) / kBlock);
+  if (st->dtype == IQSB_F64)
+    k_prob_all<double><<<grid, kBlock, 0, ctx->stream>>>((const Chunk<double> *)st->d, nchunks, log2_threads, M, ctx->d_partials);
+  else
+    k_prob_all<float><<<grid, kBlock, 0, ctx->stream>>>((const Chunk<float> *)st->d, nchunks, log2_threads, M, ctx->d_partials);
+  IQSB_TRY(iqsb_check_launch(ctx, "k_prob_all", (double)st->local_amps * st->amp_bytes()));
+  double r[kProbOut];
+  IQSB_TRY((finish<kProbOut, false>(ctx, grid, r)));
+  for (unsigned q = 0; q <= M; ++q) out[q] = r[q];
+  return IQSB_OK;
+}
+
+extern "C" int iqsb_pauli_expect(iqsb_state *st, uint64_t xmask, uint64_t ymask, uint64_t zmask, uint64_t glb_start, double out[2]) {
+  IQSB_REQUIRE(st && out, "iqsb_pauli_expect: null argument");
+  IQSB_REQUIRE(!(xmask & ymask) && !(xmask & zmask) && !(ymask & zmask), "iqsb_pauli_expect: a position carries two observables");
+  IQSB_REQUIRE(st->local_amps >= 2, "iqsb_pauli_expect: shard too small");
+  const uint64_t f = xmask | ymask;
+  IQSB_REQUIRE(f < st->local_amps, "iqsb_pauli_expect: X / Y observables must sit on local positions");
+  if (f == 0) {
+    IQSB_TRY(iqsb_parity_expect(st, zmask, glb_start, &out[0]));
+    return iqsb_norm2(st, &out[1]);
+  }
+  iqsb_ctx *ctx = st->ctx;
+  const uint64_t smask = ymask | zmask;
+  const int ny = __builtin_popcountll(ymask);
+  const uint64_t fchunk = f >> 1;
+  const int swap = (int)(f & 1);
+  double r[3] = {0., 0., 0.};
+  int grid;
+  if (fchunk == 0) {  // X or Y on position 0 only: both partners in one chunk
+    const uint64_t nwork = st->local_amps / 2;
+    grid = red_grid(ctx, nwork);
+    if (st->dtype == IQSB_F64)
+      k_pauli<double, true><<<grid, kBlock, 0, ctx->stream>>>((const Chunk<double> *)st->d, nwork, 0, 0, 0, smask, glb_start, ctx->d_partials);
+    else
+      k_pauli<float, true><<<grid, kBlock, 0, ctx->stream>>>((const Chunk<float> *)st->d, nwork, 0, 0, 0, smask, glb_start, ctx->d_partials);
+  } else {
+    const unsigned hb = 63u - (unsigned)__builtin_clzll(fchunk);
+    const uint64_t nwork = st->local_amps / 4;
+    grid = red_grid(ctx, nwork);
+    if (st->dtype == IQSB_F64)
+      k_pauli<double, false><<<grid, kBlock, 0, ctx->stream>>>((const Chunk<double> *)st->d, nwork, hb, fchunk, swap, smask, glb_start, ctx->d_partials);
+    else
+      k_pauli<float, false><<<grid, kBlock, 0, ctx->stream>>>((const Chunk<float> *)st->d, nwork, hb, fchunk, swap, smask, glb_start, ctx->d_partials);
+  }
+  IQSB_TRY(iqsb_check_launch(ctx, "k_pauli", (double)st->local_amps * st->amp_bytes()));
+  IQSB_TRY((finish<3, false>(ctx, grid, r)));
+  // <P> = Re(i^ny S); S = 2 sum s Re w (ny even) or 2 i sum s Im w (ny odd)
+  switch (ny & 3) {
+    case 0: out[0] = 2.0 * r[0]; break;
+    case 1: out[0] = -2.0 * r[1]; break;
+    case 2: out[0] = -2.0 * r[0]; break;
+    default: out[0] = 2.0 * r[1]; break;
+  }
+  out[1] = r[2];
+  return IQSB_OK;
 }
 
 template <int MODE>

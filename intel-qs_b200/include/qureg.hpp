@@ -319,6 +319,21 @@ class QubitRegister {
   unsigned lookahead_ = 0;   // unfused gates deferred for placement decisions (0: execute at once)
   mutable uint64_t exchanges_ = 0, exchanged_bits_ = 0;
 
+  // ---- one-sweep reductions (src/qureg_measure.cpp) -------------------------------------------
+  // P(bit = 1) of every physical bit, NaN = not known; valid until the next device operation or host
+  // access.  The first GetProbability after a change reads half the state (iqsb_prob1); a second
+  // one with nothing in between computes all marginals in one read (iqsb_prob_all).
+  mutable std::vector<double> marginals_;
+  mutable bool marginals_all_ = false;
+  mutable unsigned marginal_queries_ = 0;
+  mutable bool raw_exposed_ = false;  // RawState() handed the managed pointer out: no caching any more
+  void InvalidateMarginals() const {
+    marginals_all_ = false;
+    marginal_queries_ = 0;
+  }
+  static bool OneSweepReductions();  // IQS_B200_ONE_SWEEP != 0 (default on)
+  bool PauliStringReadOnly(const std::vector<unsigned> &qubits, const std::vector<unsigned> &observables, double &value, double *norm2);
+
   void InitPlacement();
   unsigned Phys(unsigned position) const { return place_.empty() ? position : place_[position]; }
   bool CanonicalPlacement() const { return !moved_; }

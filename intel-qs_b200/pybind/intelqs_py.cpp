@@ -110,6 +110,17 @@ PYBIND11_MODULE(intelqs_py, m) {
     iqsb_timer_stop(Environment::Context(), &ms);
     return ms;
   }, "B200: milliseconds since DeviceTimerStart, measured on the device");
+  m.def("DeviceSync", []() {
+    if (iqsb_sync(Environment::Context()) != IQSB_OK) throw std::runtime_error(iqsb_last_error());
+  }, "B200: wait for the engine's stream (no gate queue is flushed, no placement restored)");
+  m.def("DeviceProfile", [](bool on) {
+    if (iqsb_profile(Environment::Context(), on ? 1 : 0) != IQSB_OK) throw std::runtime_error(iqsb_last_error());
+  }, "B200: start (clearing) / stop per-kernel-class timing with CUDA events on the engine's stream");
+  m.def("DeviceProfileRead", []() {
+    std::vector<char> buf(1 << 16);
+    if (iqsb_profile_read(Environment::Context(), buf.data(), buf.size()) != IQSB_OK) throw std::runtime_error(iqsb_last_error());
+    return std::string(buf.data());
+  }, "B200: JSON text {overflow, classes: [{name, launches, ms, bytes}]} of the profiled region");
 
   py::class_<iqs::RandomNumberGenerator<double>>(m, "RandomNumberGenerator")
       .def(py::init<>())

@@ -89,6 +89,7 @@ void QubitRegister<Type>::ReleaseDevice() {
 template <class Type>
 Type *QubitRegister<Type>::HostAmplitude(std::size_t index) const {
   assert(index < LocalSize() + TmpSize());
+  InvalidateMarginals();  // the caller may write through the pointer
   if (!queue_.empty() || !CanonicalPlacement()) {
     // the host sees the state after every gate issued so far, in the reference's amplitude order
     const_cast<QubitRegister<Type> *>(this)->FlushForRead();
@@ -122,6 +123,7 @@ Type *QubitRegister<Type>::HostAmplitude(std::size_t index) const {
 
 template <class Type>
 void QubitRegister<Type>::BeforeDeviceOp() const {
+  InvalidateMarginals();  // whatever follows may change the amplitudes (or already did, from the host)
   if (managed_) {
     if (host_touched_) {
       Check(iqsb_prefetch_device(dev_), "prefetching the state back to HBM");
@@ -145,9 +147,11 @@ template <class Type>
 Type *QubitRegister<Type>::RawState() {
   FlushForRead();
   RestoreCanonicalPlacement();
+  InvalidateMarginals();
   if (managed_) {
     Check(iqsb_sync(iqs::mpi::Environment::Context()), "synchronising before a host access");
     host_touched_ = true;
+    raw_exposed_ = true;  // the pointer may be kept and written through at any time (NumPy views)
     return state;
   }
   // device-memory register: hand out the mirror with every chunk checked out

@@ -8,7 +8,7 @@
 //       -> intel-qs_b200/bin/iqs_b200_driver (the drop-in proof: no source change)
 //
 // usage: driver <program.bin> [--state-in s.bin] [--state-out s.bin] [--scalars-out x.bin]
-//               [--map-out m.bin] [--repeat R] [--step-sizes a,b,c]
+//               [--map-out m.bin] [--repeat R] [--step-sizes a,b,c] [--no-step-norm]
 // Prints one line "TIME <seconds> OPS <count>" for the timed replay (init excluded).
 #include <chrono>
 #include <cstdio>
@@ -155,6 +155,7 @@ int main(int argc, char **argv) {
   }
   const char *state_in = nullptr, *state_out = nullptr, *scalars_out = nullptr, *map_out = nullptr;
   int repeat = 1;
+  bool step_norm = true;
   std::vector<std::size_t> step_sizes;
   for (int i = 2; i < argc; ++i) {
     std::string a = argv[i];
@@ -163,6 +164,7 @@ int main(int argc, char **argv) {
     else if (a == "--scalars-out" && i + 1 < argc) scalars_out = argv[++i];
     else if (a == "--map-out" && i + 1 < argc) map_out = argv[++i];
     else if (a == "--repeat" && i + 1 < argc) repeat = atoi(argv[++i]);
+    else if (a == "--no-step-norm") step_norm = false;  // synchronous engines (the reference) need no closing reduction
     else if (a == "--step-sizes" && i + 1 < argc) {  // comma separated op counts, one per timed step
       std::string list = argv[++i];
       for (std::size_t p = 0; p < list.size();) {
@@ -214,7 +216,7 @@ int main(int argc, char **argv) {
       std::vector<iqs_op> part(ops.begin() + first, ops.begin() + last);
       auto s0 = std::chrono::steady_clock::now();
       run_ops(psi, part, scalars);
-      psi.ComputeNorm();
+      if (step_norm) psi.ComputeNorm();
       auto s1 = std::chrono::steady_clock::now();
       if (iqs::mpi::Environment::GetStateRank() == 0)
         printf("STEP %zu %.6f\n", s, std::chrono::duration<double>(s1 - s0).count());

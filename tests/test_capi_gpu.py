@@ -401,6 +401,68 @@ def test_small_fused_tiles(gpu_ctx, oracle):
         st.free()
 
 
+def _pauli_expect_numpy(psi, n, xmask, ymask, zmask):
+    """<psi|P|psi> from the definition: P|i> = i^ny (-1)^popcount(i & (y|z)) |i ^ (x|y)>"""
+    idx = np.arange(1 << n, dtype=np.uint64)
+    f, m = np.uint64(xmask | ymask), np.uint64(ymask | zmask)
+    par = np.zeros(1 << n, dtype=np.int64)
+    t = idx & m
+    for b in range(n):
+        par ^= ((t >> np.uint64(b)) & np.uint64(1)).astype(np.int64)
+    sign = 1.0 - 2.0 * par
+    ny = bin(ymask).count("1")
+    val = (1j ** ny) * np.sum(sign * psi * np.conj(psi[idx ^ f]))
+    assert abs(val.imag) < 1e-12
+    return val.real
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 13, 20])
+def test_all_marginals_in_one_sweep(gpu_ctx, oracle, n):
+    """iqsb_prob_all == [norm, prob1(0), prob1(1), ...] (oracle: the reference's GetProbability sum)"""
+    st = gpu_ctx.alloc(1 << n)
+    psi = C.random_state(n, seed=50 + n)
+    st.upload(psi)
+    got = st.prob_all()
+    assert got.shape == (n + 1,)
+    assert abs(got[0] - 1.0) <= TOL
+    for q in range(n):
+        assert abs(got[1 + q] - oracle.prob1(psi, q)) <= TOL, q
+        if n >= 2 or q > 0:
+            assert abs(got[1 + q] - st.prob1(q)) <= TOL
+    assert np.array_equal(st.download(), psi)  # nothing written
+    st.free()
+
+
+@pytest.mark.parametrize("n", [1, 2, 6, 14])
+def test_pauli_string_expectation_is_read_only_and_matches_definition(gpu_ctx, n):
+    st = gpu_ctx.alloc(1 << n)
+    psi = C.random_state(n, seed=70 + n)
+    st.upload(psi)
+    rng = np.random.Generator(np.random.MT19937(n))
+    cases = [(1, 0, 0), (0, 1, 0), (0, 0, 1)]
+    if n >= 2:
+        cases += [(1, 2, 0), (2, 1, 0), (3, 0, 0), (0, 3, 0), (1 << (n - 1), 0, 1), (0, 1 << (n - 1), 1), (1 << (n - 1), 1, 0)]
+    for _ in range(12 if n > 2 else 0):
+        obs = rng.integers(0, 4, size=n)
+        cases.append(tuple(int(sum(1 << q for q in range(n) if obs[q] == k)) for k in (1, 2, 3)))
+    for xm, ym, zm in cases:
+        if n == 1 and (xm | ym) == 0:
+            continue
+        got, norm2 = st.pauli_expect(xm, ym, zm, with_norm=True)
+        want = _pauli_expect_numpy(psi, n, xm, ym, zm)
+        assert abs(got - want) <= TOL, (xm, ym, zm, got, want)
+        assert abs(norm2 - 1.0) <= TOL  # sum |a|^2 comes out of the same read
+    # a Z factor on a rank bit is taken from glb_start
+    if n >= 2:
+        hi = 1 << n
+        got = st.pauli_expect(1, 0, hi | 2, glb_start=hi)
+        assert abs(got + _pauli_expect_numpy(psi, n, 1, 0, 2)) <= TOL
+    assert np.array_equal(st.download(), psi)
+    with pytest.raises(capi.IqsbError):
+        st.pauli_expect(1 << n, 0, 0)  # X on a rank bit is not this kernel's job
+    st.free()
+
+
 def _class_matrices():
     """one matrix per arithmetic class of the fused kernel (kernels_fused.cu: classify)"""
     f = 1.0 / math.sqrt(2.0)

@@ -85,10 +85,50 @@ def test_auto_fusion_env_is_transparent(oracle):
     prog.extend(random_program(n, 60, seed + 2))
     psi = C.random_state(n, seed)
     want, wsc, wmap = oracle.run_program(n, psi, prog.ops)
-    got = run_gpu(oracle, prog, state=psi, extra_env={"IQS_B200_AUTO_FUSION": "1"})
+    # the reference's ExpectationValue rotates the state into the observable's basis and back (two
+    # roundings per amplitude); IQS_B200_ONE_SWEEP=0 does the same sweeps, so the states are identical
+    got = run_gpu(oracle, prog, state=psi, extra_env={"IQS_B200_AUTO_FUSION": "1", "IQS_B200_ONE_SWEEP": "0"})
     assert np.array_equal(got["map"], wmap)
     assert np.max(np.abs(got["scalars"] - wsc)) <= TOL
     assert np.array_equal(got["state"], want)
+    # default: read-only expectation values (the state is not touched at all), same numbers to 1e-12
+    got = run_gpu(oracle, prog, state=psi, extra_env={"IQS_B200_AUTO_FUSION": "1"})
+    assert np.max(np.abs(got["scalars"] - wsc)) <= TOL
+    assert np.max(np.abs(got["state"] - want)) <= TOL
+
+
+def test_one_sweep_reductions_through_the_api(oracle):
+    """GetProbability of every qubit (all marginals from one read after the first call), every
+    1- and 2-qubit Pauli expectation wrapper and longer strings -- the reference's table
+    (unit_test/include/expectation_values_test.hpp:121-239) on a random state, permuted register."""
+    n, seed = 11, 17
+    rng = np.random.default_rng(seed)
+    prog = random_program(n, 120, seed)
+    prog.permute(list(rng.permutation(n)))
+    for rep in range(2):
+        for q in range(n):
+            prog.prob(q)
+        for o in (1, 2, 3):
+            for q in (0, 4, n - 1):
+                prog.expect1(q, o)
+        for o1 in (1, 2, 3):
+            for o2 in (1, 2, 3):
+                prog.expect([2, 7], [o1, o2]).expect([n - 1, 0], [o1, o2])
+        prog.expect(list(range(n)), [1 + (q % 3) for q in range(n)])
+        prog.expect([1, 3, 5, 8], [2, 2, 2, 1])
+        for q in range(n):
+            prog.prob(n - 1 - q)
+        prog.named1(C.H, 3).prob(3).prob(0)  # a gate invalidates the cached marginals
+    prog.norm()
+    psi = C.random_state(n, seed)
+    want, wsc, wmap = oracle.run_program(n, psi, prog.ops)
+    got = run_gpu(oracle, prog, state=psi)
+    assert len(got["scalars"]) == len(wsc)
+    assert np.max(np.abs(got["scalars"] - wsc)) <= TOL
+    assert np.max(np.abs(got["state"] - want)) <= TOL
+    ref_like = run_gpu(oracle, prog, state=psi, extra_env={"IQS_B200_ONE_SWEEP": "0"})
+    assert np.max(np.abs(ref_like["scalars"] - wsc)) <= TOL
+    assert np.array_equal(ref_like["state"], want)
 
 
 def test_spec_modes_do_not_change_results(oracle):

@@ -5,12 +5,9 @@ set -e
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()" >/dev/null
 variants=(
-  "sync:-DIQSB_FUSED_ASYNC_LOAD=0"
-  "async:"
-  "async_l2:-DIQSB_FUSED_LOADS=2"
-  "async_mb4:-DIQSB_FUSED_MINBLOCKS=4 -DIQSB_FUSED_LOADS=2"
-  "async_t11mb4:-DIQSB_FUSED_TILE=11 -DIQSB_FUSED_MINBLOCKS=4"
-  "async_t11mb5:-DIQSB_FUSED_TILE=11 -DIQSB_FUSED_MINBLOCKS=5 -DIQSB_FUSED_LOADS=2"
+  "t11dbuf:"
+  "t12single:-DIQSB_FUSED_DBUF=0"
+  "t11single_mb5:-DIQSB_FUSED_DBUF=0 -DIQSB_FUSED_TILE=11 -DIQSB_FUSED_MINBLOCKS=3"
 )
 for v in "${variants[@]}"; do
   name=${v%%:*}; flags=${v#*:}

@@ -117,6 +117,13 @@ def main():
             gates = [((1, int(op["q0"]), int(op["q1"])) if op["kind"] == C.CX else (0, 0, int(op["q0"]))) + (bench.named_matrix(C, int(op["kind"]), op["p"]),) for op in layer]
             runs = len(capi.plan_fused_order(gates, n))
             timeit(f"bench_layer{li}_{len(gates)}g{runs}r", "-", lambda gates=gates: st.fused(gates), 32.0 * L * runs)
+    if "fusedprof" in ops:  # the profiling target: one bench layer (named 1-qubit gates + CNOT ladder) as one fused call
+        import bench
+
+        layer = bench.build_layers(C, n, 1)[0]
+        gates = [((1, int(op["q0"]), int(op["q1"])) if op["kind"] == C.CX else (0, 0, int(op["q0"]))) + (bench.named_matrix(C, int(op["kind"]), op["p"]),) for op in layer]
+        runs = len(capi.plan_fused_order(gates, n))
+        timeit(f"bench_layer0_{len(gates)}g{runs}r", "-", lambda gates=gates: st.fused(gates), 32.0 * L * runs)
     if "gate2" in ops:
         rng = np.random.default_rng(0)
         q, _ = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))

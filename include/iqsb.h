@@ -39,7 +39,7 @@ enum {
   IQSB_MEM_DEVICE = 0, /* cudaMalloc: fastest, IPC-exportable (needed for nranks > 1)  */
   IQSB_MEM_MANAGED = 1 /* cudaMallocManaged, device-preferred: host pointer is valid   */
 };
-enum { IQSB_OK = 0, IQSB_ERR_CUDA = -1, IQSB_ERR_NCCL = -2, IQSB_ERR_ARG = -3, IQSB_ERR_STATE = -4 };
+enum { IQSB_OK = 0, IQSB_ERR_CUDA = -1, IQSB_ERR_NCCL = -2, IQSB_ERR_ARG = -3, IQSB_ERR_STATE = -4, IQSB_ERR_PEER = -5 };
 enum { IQSB_SUM = 0, IQSB_MAX = 1 };
 #define IQSB_UNIQUE_ID_BYTES 128
 
@@ -76,6 +76,12 @@ int iqsb_set_arith(iqsb_ctx *ctx, int mode);
 int iqsb_get_arith(const iqsb_ctx *ctx);
 /* number of kernels this context launched since creation (bench.py: gpu_launches). */
 uint64_t iqsb_launch_count(const iqsb_ctx *ctx);
+/* Errors raised on the device since the context was created: IQSB_ERR_PEER when a rendezvous between
+ * GPUs (the flag barrier that brackets every peer-memory kernel) gave up because a partner did not
+ * arrive within IQS_B200_BARRIER_TIMEOUT_S seconds (default 300, 0 = wait for ever) -- the reference's
+ * MPI job would hang in MPI_Sendrecv there.  Also returned by iqsb_sync, iqsb_barrier and every
+ * reduction, which is where a program notices. */
+int iqsb_check(iqsb_ctx *ctx);
 /* Per-kernel-class device timing with CUDA events on the engine's stream (what bench.py's roofline
  * block is computed from; the reference's counterpart is the Timer of include/timer.hpp, filled by
  * QubitRegister::EnableStatistics).  iqsb_profile(ctx, 1) clears and starts, iqsb_profile(ctx, 0)
@@ -314,6 +320,10 @@ int iqsb_idle_global(iqsb_state *st);
 /* whole-shard move: this rank's shard goes to `dst_rank`, it receives `src_rank`'s:
  * replaces the Sendrecv loop of PermuteGlobalQubits (src/qureg_permute.cpp:174-185) */
 int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank);
+/* the same move described by the permutation of the rank bits (content of rank bit b goes to rank bit
+ * dst_rank_bit[b], nbits = log2(nranks)): every rank derives its source, its destination and the
+ * path all ranks take from the table -- no collective is needed to agree. */
+int iqsb_permute_global_bits(iqsb_state *st, const uint8_t *dst_rank_bit, unsigned nbits);
 /* bytes this context moved over NVLink (peer loads + peer stores) since creation. */
 uint64_t iqsb_nvlink_bytes(const iqsb_ctx *ctx);
 

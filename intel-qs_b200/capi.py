@@ -157,6 +157,7 @@ def load():
         "iqsb_set_stream": [c_vp, c_vp], "iqsb_get_stream": [c_vp], "iqsb_set_arith": [c_vp, c_int], "iqsb_get_arith": [c_vp],
         "iqsb_launch_count": [c_vp], "iqsb_nvlink_bytes": [c_vp],
         "iqsb_prob_all": [c_vp, c_vp, c_int], "iqsb_pauli_expect": [c_vp, c_u64, c_u64, c_u64, c_u64, c_vp],
+        "iqsb_check": [c_vp],
         "iqsb_profile": [c_vp, c_int], "iqsb_profile_read": [c_vp, c_vp, ctypes.c_size_t],
         "iqsb_timer_start": [c_vp], "iqsb_timer_stop": [c_vp, ctypes.POINTER(c_dbl)],
         "iqsb_event_record": [c_vp, c_int], "iqsb_event_elapsed": [c_vp, c_int, c_int, ctypes.POINTER(c_dbl)],
@@ -208,7 +209,7 @@ def load():
         "iqsb_gate1_global": [c_vp, c_uint, c_uint, c_vp],
         "iqsb_cgate1_global": [c_vp, c_uint, c_uint, c_uint, c_vp],
         "iqsb_swap2x2_global": [c_vp, c_uint, c_uint, c_uint, c_vp],
-        "iqsb_permute_global": [c_vp, c_int, c_int],
+        "iqsb_permute_global": [c_vp, c_int, c_int], "iqsb_permute_global_bits": [c_vp, c_vp, c_uint],
         "iqsb_exchange_bits": [c_vp, c_uint, c_int, c_vp, c_vp],
         "iqsb_plan_exchange": [c_int, c_int, c_uint, c_int, c_vp, c_vp, c_vp],
         "iqsb_plan_placement": [c_vp, c_uint, c_uint, c_vp, c_int, c_u64, c_vp, c_uint, c_vp, c_vp, ctypes.POINTER(c_int)],
@@ -288,6 +289,10 @@ class Context:
 
     def nvlink_bytes(self):
         return int(self.L.iqsb_nvlink_bytes(self.h))
+
+    def check(self):
+        """raises IqsbError if a kernel reported a failure (peer barrier deadline)"""
+        _chk(self.L.iqsb_check(self.h))
 
     def profile(self, on):
         """start (clearing) / stop the per-kernel-class device timing"""
@@ -538,3 +543,7 @@ class State:
 
     def permute_global(self, src_rank, dst_rank):
         _chk(self.L.iqsb_permute_global(self.h, src_rank, dst_rank))
+
+    def permute_global_bits(self, dst_rank_bit):
+        a = np.ascontiguousarray(dst_rank_bit, dtype=np.uint8)
+        _chk(self.L.iqsb_permute_global_bits(self.h, a.ctypes.data_as(c_vp), a.size))

@@ -158,6 +158,9 @@ extern "C" int iqsb_init(int rank, int nranks, const void *uid, int device, iqsb
   IQSB_CUDA(cudaMalloc(&ctx->d_result, sizeof(double) * kMaxRedOut));
   IQSB_CUDA(cudaMalloc(&ctx->d_flags, sizeof(int) * 4));
   IQSB_CUDA(cudaMallocHost(&ctx->h_result, sizeof(double) * kMaxRedOut));
+  IQSB_CUDA(cudaHostAlloc((void **)&ctx->h_status, sizeof(int), cudaHostAllocMapped));
+  *ctx->h_status = IQSB_OK;
+  IQSB_CUDA(cudaHostGetDevicePointer((void **)&ctx->d_status, ctx->h_status, 0));
   if (const char *a = getenv("IQS_B200_ARITH")) ctx->arith = (strcmp(a, "fma") == 0 || strcmp(a, "FMA") == 0) ? IQSB_ARITH_FMA : IQSB_ARITH_EXACT;
   if (nranks > 1) {
     int rc = iqsb_comm_init(ctx, uid);
@@ -182,6 +185,7 @@ extern "C" int iqsb_finalize(iqsb_ctx *ctx) {
   cudaFree(ctx->d_result);
   cudaFree(ctx->d_flags);
   cudaFreeHost(ctx->h_result);
+  cudaFreeHost(ctx->h_status);
   cudaFreeHost(ctx->stage_h);
   cudaFree(ctx->stage_d);
   cudaFree(ctx->d_tile_counter);
@@ -207,10 +211,23 @@ extern "C" int iqsb_device(const iqsb_ctx *ctx) { return ctx ? ctx->device : -1;
 extern "C" uint64_t iqsb_launch_count(const iqsb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" uint64_t iqsb_nvlink_bytes(const iqsb_ctx *ctx) { return ctx ? ctx->nvlink_bytes : 0; }
 
+// What the kernels reported since the last call: today only the peer barrier, which gives up after
+// IQS_B200_BARRIER_TIMEOUT_S seconds without a partner instead of spinning for ever.
+extern "C" int iqsb_check(iqsb_ctx *ctx) {
+  IQSB_REQUIRE(ctx, "iqsb_check: null context");
+  const int st = ctx->h_status ? *(volatile int *)ctx->h_status : IQSB_OK;
+  if (st != IQSB_OK) {
+    iqsb_set_error("rank %d: a peer did not reach the barrier within %.0f s (or another rank gave up first); the ranks are out of step and the state is undefined",
+                   ctx->rank, ctx->barrier_timeout_s);
+    return st;
+  }
+  return IQSB_OK;
+}
+
 extern "C" int iqsb_sync(iqsb_ctx *ctx) {
   IQSB_REQUIRE(ctx, "iqsb_sync: null context");
   IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
-  return IQSB_OK;
+  return iqsb_check(ctx);
 }
 
 extern "C" int iqsb_mem_info(iqsb_ctx *ctx, uint64_t *free_bytes, uint64_t *total_bytes) {

@@ -82,7 +82,7 @@ static bool load() {
 
 struct iqsb_peer_table {
   ncclComm_t comm = nullptr;
-  uint32_t *flags_local = nullptr;  // [nranks] on this GPU; slot r is written by rank r
+  uint32_t *flags_local = nullptr;  // [nranks + 1] on this GPU; slot r is written by rank r, slot nranks is the abort word
   uint32_t **flags_peer = nullptr;  // host array: peer-mapped pointer to every rank's flags
   uint32_t **d_flags_peer = nullptr;
   uint32_t epoch = 0;
@@ -94,18 +94,43 @@ namespace {
 
 constexpr int kMaxCollDoubles = 64;
 
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Every rank stores `epoch` into slot `me` of every peer's flag array, then waits until all
 // of its own slots reached `epoch`.  Kernel boundaries on the stream order it after the
 // preceding gate kernel; the system fence publishes that kernel's peer stores first.
-__global__ void k_barrier(uint32_t *const *peer_flags, volatile uint32_t *my_flags, int me, int nranks, uint32_t epoch) {
+//
+// A rank that died (or never arrives) must not hang the other GPUs for ever: the wait has a
+// wall-clock deadline.  The rank whose deadline passes raises the abort word (slot nranks) on every
+// rank and records IQSB_ERR_PEER in its status word; every spinning rank sees its abort word, stops
+// and records the same.  From then on barriers return at once -- the ordering guarantee is gone and
+// the host gets the error from the next call that synchronises (iqsb_sync, iqsb_barrier, any
+// reduction; iqsb_check at any time).
+__global__ void k_barrier(uint32_t *const *peer_flags, volatile uint32_t *my_flags, int me, int nranks, uint32_t epoch, uint64_t timeout_ns,
+                          volatile int *status) {
   int r = threadIdx.x;
   if (r < nranks && r != me) {
     __threadfence_system();
     volatile uint32_t *dst = peer_flags[r] + me;
     *dst = epoch;
     __threadfence_system();
+    const uint64_t t0 = global_ns();
+    unsigned spins = 0;
+    bool failed = false;
     while ((int32_t)(my_flags[r] - epoch) < 0) {
+      if (my_flags[nranks] != 0u) { failed = true; break; }  // somebody gave up
+      if ((++spins & 1023u) == 0u && timeout_ns != 0 && global_ns() - t0 > timeout_ns) {
+        for (int q = 0; q < nranks; ++q) *(volatile uint32_t *)(peer_flags[q] + nranks) = 1u + (uint32_t)r;  // who was missing, +1
+        __threadfence_system();
+        failed = true;
+        break;
+      }
     }
+    if (failed) *status = IQSB_ERR_PEER;
     __threadfence_system();
   }
 }
@@ -201,6 +226,7 @@ extern "C" int iqsb_unique_id(void *out_128_bytes) {
 }
 
 int iqsb_comm_init(iqsb_ctx *ctx, const void *uid) {
+  IQSB_REQUIRE(ctx->nranks <= 32, "iqsb_init: at most 32 ranks (the barrier kernel signals one peer per lane), %d requested", ctx->nranks);
   iqsb_peer_table *pt = new iqsb_peer_table();
   ctx->peers = pt;
   ncclUniqueId id;
@@ -213,8 +239,9 @@ int iqsb_comm_init(iqsb_ctx *ctx, const void *uid) {
   ctx->comm = pt->comm;
   IQSB_CUDA(cudaMalloc(&pt->d_coll, sizeof(double) * kMaxCollDoubles));
   IQSB_CUDA(cudaMalloc(&pt->d_handles, 64 * ctx->nranks));
-  IQSB_CUDA(cudaMalloc(&pt->flags_local, sizeof(uint32_t) * ctx->nranks));
-  IQSB_CUDA(cudaMemset(pt->flags_local, 0, sizeof(uint32_t) * ctx->nranks));
+  IQSB_CUDA(cudaMalloc(&pt->flags_local, sizeof(uint32_t) * (ctx->nranks + 1)));
+  IQSB_CUDA(cudaMemset(pt->flags_local, 0, sizeof(uint32_t) * (ctx->nranks + 1)));
+  if (const char *e = getenv("IQS_B200_BARRIER_TIMEOUT_S")) ctx->barrier_timeout_s = atof(e);
   pt->flags_peer = new uint32_t *[ctx->nranks];
   IQSB_TRY(open_peers(ctx, pt->flags_local, (void **)pt->flags_peer));
   IQSB_CUDA(cudaMalloc(&pt->d_flags_peer, sizeof(uint32_t *) * ctx->nranks));
@@ -248,7 +275,8 @@ static int peer_barrier(iqsb_ctx *ctx) { return iqsb_peer_barrier(ctx); }
 int iqsb_peer_barrier(iqsb_ctx *ctx) {
   iqsb_peer_table *pt = ctx->peers;
   pt->epoch++;
-  k_barrier<<<1, 32, 0, ctx->stream>>>(pt->d_flags_peer, pt->flags_local, ctx->rank, ctx->nranks, pt->epoch);
+  const uint64_t timeout_ns = ctx->barrier_timeout_s > 0. ? (uint64_t)(ctx->barrier_timeout_s * 1e9) : 0ull;
+  k_barrier<<<1, 32, 0, ctx->stream>>>(pt->d_flags_peer, pt->flags_local, ctx->rank, ctx->nranks, pt->epoch, timeout_ns, ctx->d_status);
   return iqsb_check_launch(ctx, "k_barrier");
 }
 
@@ -256,7 +284,7 @@ extern "C" int iqsb_barrier(iqsb_ctx *ctx) {
   IQSB_REQUIRE(ctx, "iqsb_barrier: null context");
   if (ctx->nranks > 1) IQSB_TRY(peer_barrier(ctx));
   IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
-  return IQSB_OK;
+  return iqsb_check(ctx);
 }
 
 extern "C" int iqsb_allreduce_f64(iqsb_ctx *ctx, double *inout, int n, int op) {
@@ -453,8 +481,10 @@ extern "C" int iqsb_idle_global(iqsb_state *st) {
   return peer_barrier(ctx);
 }
 
-extern "C" int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank) {
-  IQSB_REQUIRE(st, "iqsb_permute_global: null argument");
+// pairwise < 0: not known -- the ranks agree through a 1-double all-reduce (iqsb_permute_global, where
+// each rank only knows its own source and destination); 0 / 1: decided by the caller from the
+// permutation of the rank bits, which every rank knows (iqsb_permute_global_bits): no communication.
+static int permute_global_impl(iqsb_state *st, int src_rank, int dst_rank, int pairwise) {
   iqsb_ctx *ctx = st->ctx;
   IQSB_REQUIRE(ctx->nranks > 1 && st->shared, "iqsb_permute_global: register is not shared across ranks");
   IQSB_REQUIRE(src_rank >= 0 && src_rank < ctx->nranks && dst_rank >= 0 && dst_rank < ctx->nranks, "iqsb_permute_global: bad ranks");
@@ -462,10 +492,11 @@ extern "C" int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank) {
   // Fast path: when every rank is a fixed point or half of a 2-cycle (e.g. reversing the order of the
   // global qubits), partners exchange their shards in place with one kernel each -- the lower rank
   // swaps the upper half, the higher rank the lower half -- without staging.  All ranks must take the
-  // same path (the rendezvous counts differ), so they agree through a 1-double all-reduce.
+  // same path (the rendezvous counts differ).
   {
     double not_simple = (src_rank == dst_rank) ? 0.0 : 1.0;
-    IQSB_TRY(iqsb_allreduce_f64(ctx, &not_simple, 1, IQSB_MAX));
+    if (pairwise < 0) IQSB_TRY(iqsb_allreduce_f64(ctx, &not_simple, 1, IQSB_MAX));
+    else not_simple = pairwise ? 0.0 : 1.0;
     if (not_simple == 0.0 && Lall >= 4) {
       IQSB_TRY(peer_barrier(ctx));
       if (src_rank != ctx->rank) {
@@ -522,4 +553,36 @@ extern "C" int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank) {
     cudaFree(owned);
   }
   return rc;
+}
+
+extern "C" int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank) {
+  IQSB_REQUIRE(st, "iqsb_permute_global: null argument");
+  return permute_global_impl(st, src_rank, dst_rank, -1);
+}
+
+// The content of rank bit b moves to rank bit dst_rank_bit[b].  Every rank derives its own source and
+// destination AND whether all ranks move in pairs (the bit permutation is an involution) from the same
+// table: nothing has to be agreed at run time.
+extern "C" int iqsb_permute_global_bits(iqsb_state *st, const uint8_t *dst_rank_bit, unsigned nbits) {
+  IQSB_REQUIRE(st && dst_rank_bit, "iqsb_permute_global_bits: null argument");
+  iqsb_ctx *ctx = st->ctx;
+  IQSB_REQUIRE(nbits < 31 && (1 << nbits) == ctx->nranks, "iqsb_permute_global_bits: %u rank bits do not describe %d ranks", nbits, ctx->nranks);
+  unsigned inverse[32], seen = 0;
+  for (unsigned b = 0; b < nbits; ++b) {
+    IQSB_REQUIRE(dst_rank_bit[b] < nbits && !((seen >> dst_rank_bit[b]) & 1u), "iqsb_permute_global_bits: not a permutation of the rank bits");
+    seen |= 1u << dst_rank_bit[b];
+    inverse[dst_rank_bit[b]] = b;
+  }
+  bool involution = true, identity = true;
+  int destination = 0, source = 0;
+  for (unsigned b = 0; b < nbits; ++b) {
+    involution = involution && dst_rank_bit[dst_rank_bit[b]] == b;
+    identity = identity && dst_rank_bit[b] == b;
+    if ((ctx->rank >> b) & 1) {
+      destination |= 1 << dst_rank_bit[b];  // my bit b travels to bit dst[b]
+      source |= 1 << inverse[b];            // my bit b is filled from bit inverse[b] of the source rank
+    }
+  }
+  if (identity) return IQSB_OK;
+  return permute_global_impl(st, source, destination, involution ? 1 : 0);
 }

@@ -69,6 +69,10 @@ struct iqsb_ctx {
   int arith = IQSB_ARITH_EXACT;  // iqsb_set_arith
   iqsb_prof *prof = nullptr;     // iqsb_profile
   unsigned long long *d_tile_counter = nullptr;  // tile scheduler of the fused kernel
+  // status word written by kernels that give up (the peer barrier's deadline): pinned host memory
+  // mapped into the device, read by iqsb_check
+  int *h_status = nullptr, *d_status = nullptr;
+  double barrier_timeout_s = 300.;  // IQS_B200_BARRIER_TIMEOUT_S; 0 = wait for ever
 };
 constexpr size_t kStageBytes = 1u << 20;
 
@@ -215,9 +219,10 @@ struct Geom {
   uint64_t off0, off1;  // added to the expanded index for the two partners
 };
 
+// (an unused Geom slot carries p = 63: the two-step shift keeps every shift count below 64)
 __device__ __forceinline__ uint64_t insert_zero(uint64_t x, unsigned p) {
   uint64_t low = x & ((1ull << p) - 1ull);
-  return ((x >> p) << (p + 1)) | low;
+  return (((x >> p) << p) << 1) | low;
 }
 __device__ __forceinline__ uint64_t expand(uint64_t t, const Geom &g) {
   uint64_t x = insert_zero(t, g.ins0);

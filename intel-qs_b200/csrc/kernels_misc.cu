@@ -235,7 +235,14 @@ extern "C" int iqsb_axpy(iqsb_state *a, const iqsb_state *b, const double f[2]) 
   IQSB_REQUIRE(a && b && f, "iqsb_axpy: null argument");
   IQSB_REQUIRE(a->local_amps == b->local_amps && a->dtype == b->dtype && a->ctx == b->ctx,
                "iqsb_axpy: registers do not match");
-  IQSB_REQUIRE(a->local_amps >= 2, "iqsb_axpy: shard too small");
+  if (a->local_amps == 1) {  // the reference's default-constructed register: one amplitude, on the host
+    double xr, xi, yr, yi;
+    IQSB_TRY(iqsb_get_amp(a, 0, &xr, &xi));
+    IQSB_TRY(iqsb_get_amp(const_cast<iqsb_state *>(b), 0, &yr, &yi));
+    if (a->dtype == IQSB_F64) return iqsb_set_amp(a, 0, xr + (f[0] * yr - f[1] * yi), xi + (f[0] * yi + f[1] * yr));
+    const float fr = (float)f[0], fi = (float)f[1], br = (float)yr, bi = (float)yi;
+    return iqsb_set_amp(a, 0, (float)xr + (fr * br - fi * bi), (float)xi + (fr * bi + fi * br));
+  }
   iqsb_ctx *ctx = a->ctx;
   uint64_t nchunks = a->local_amps / 2;
   int grid = stream_grid(ctx, nchunks);

@@ -341,7 +341,7 @@ int finish(iqsb_ctx *ctx, int nblocks, double *out) {
   IQSB_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, NOUT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int k = 0; k < NOUT; ++k) out[k] = ctx->h_result[k];
-  return IQSB_OK;
+  return iqsb_check(ctx);
 }
 
 int fetch_flags(iqsb_ctx *ctx, int n, int *out) {
@@ -481,7 +481,21 @@ static int two_reg(iqsb_state *a, iqsb_state *b, const double f[2], double *out)
   IQSB_REQUIRE(a && b && out, "two-register reduction: null argument");
   IQSB_REQUIRE(a->local_amps == b->local_amps && a->dtype == b->dtype && a->ctx == b->ctx,
                "two-register reduction: registers do not match");
-  IQSB_REQUIRE(a->local_amps >= 2, "two-register reduction: shard too small");
+  if (a->local_amps == 1) {  // the reference's default-constructed register: one amplitude, on the host
+    double xr, xi, yr, yi;
+    IQSB_TRY(iqsb_get_amp(a, 0, &xr, &xi));
+    IQSB_TRY(iqsb_get_amp(b, 0, &yr, &yi));
+    if (MODE == 0) {  // conj(b) a
+      out[0] = yr * xr + yi * xi;
+      out[1] = yr * xi - yi * xr;
+    } else if (MODE == 1) {
+      const double fr = f[0] * yr - f[1] * yi, fi = f[0] * yi + f[1] * yr;
+      out[0] = hypot(xr - fr, xi - fi);
+    } else {
+      out[0] = (xr - yr) * (xr - yr) + (xi - yi) * (xi - yi);
+    }
+    return IQSB_OK;
+  }
   iqsb_ctx *ctx = a->ctx;
   uint64_t nchunks = a->local_amps / 2;
   int grid = red_grid(ctx, nchunks);
@@ -529,7 +543,13 @@ extern "C" int iqsb_equal(iqsb_state *a, iqsb_state *b, int *out) {
   IQSB_REQUIRE(a && b && out, "iqsb_equal: null argument");
   IQSB_REQUIRE(a->local_amps == b->local_amps && a->dtype == b->dtype && a->ctx == b->ctx,
                "iqsb_equal: registers do not match");
-  IQSB_REQUIRE(a->local_amps >= 2, "iqsb_equal: shard too small");
+  if (a->local_amps == 1) {
+    double xr, xi, yr, yi;
+    IQSB_TRY(iqsb_get_amp(a, 0, &xr, &xi));
+    IQSB_TRY(iqsb_get_amp(b, 0, &yr, &yi));
+    *out = (xr == yr && xi == yi) ? 1 : 0;
+    return IQSB_OK;
+  }
   iqsb_ctx *ctx = a->ctx;
   IQSB_CUDA(cudaMemsetAsync(ctx->d_flags, 0, 4 * sizeof(int), ctx->stream));
   uint64_t nchunks = a->local_amps / 2;

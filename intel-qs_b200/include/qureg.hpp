@@ -347,6 +347,8 @@ class QubitRegister {
   void BringLocal(std::size_t queue_from, uint64_t protect_mask);
   void SwapPlacement(unsigned position_a, unsigned position_b);
   void RestoreCanonicalPlacement() const;
+  void Relabel(const Permutation &target);  // src/qureg_permute.cpp: a permutation is a relabelling first
+  void SettleAfterRelabel();
   void AlignPlacement(QubitRegister &other);
   std::size_t PhysicalIndex(std::size_t data_index) const;
 

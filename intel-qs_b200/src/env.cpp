@@ -6,6 +6,7 @@
 #include <cassert>
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <iostream>
 #include <string>
@@ -144,19 +145,35 @@ void Environment::Bootstrap() {
     const char *port = getenv("MASTER_PORT");
     file = std::string("/dev/shm/iqs_b200_uid_") + (port ? std::string(port) : toString((long)getppid()));
   }
+  // Rendezvous file: the NCCL id followed by the wall-clock second rank 0 wrote it.  A file left behind
+  // by a run that died (same MASTER_PORT, predictable name in a shared directory) is recognised by its
+  // age and skipped instead of being used for a bootstrap that can never complete: rank 0 removes
+  // whatever it finds before publishing, the others only accept a stamp from the last two minutes.
   unsigned char uid[IQSB_UNIQUE_ID_BYTES];
+  const long long kMaxAgeSeconds = 120;
   if (rank == 0) {
+    remove(file.c_str());
     if (iqsb_unique_id(uid) != IQSB_OK) die("cannot create the NCCL unique id");
     std::string tmp = file + ".tmp";
     FILE *fp = fopen(tmp.c_str(), "wb");
-    if (!fp || fwrite(uid, 1, sizeof(uid), fp) != sizeof(uid)) throw std::runtime_error("cannot write " + tmp);
+    long long stamp = (long long)time(nullptr);
+    if (!fp || fwrite(uid, 1, sizeof(uid), fp) != sizeof(uid) || fwrite(&stamp, sizeof(stamp), 1, fp) != 1) throw std::runtime_error("cannot write " + tmp);
     fclose(fp);
     rename(tmp.c_str(), file.c_str());
   } else {
-    FILE *fp = nullptr;
-    for (int tries = 0; tries < 6000 && !(fp = fopen(file.c_str(), "rb")); ++tries) std::this_thread::sleep_for(std::chrono::milliseconds(10));
-    if (!fp || fread(uid, 1, sizeof(uid), fp) != sizeof(uid)) throw std::runtime_error("cannot read the NCCL id from " + file);
-    fclose(fp);
+    bool have = false;
+    for (int tries = 0; tries < 6000 && !have; ++tries) {
+      if (FILE *fp = fopen(file.c_str(), "rb")) {
+        long long stamp = 0;
+        const bool complete = fread(uid, 1, sizeof(uid), fp) == sizeof(uid);
+        const bool stamped = complete && fread(&stamp, sizeof(stamp), 1, fp) == 1;
+        fclose(fp);
+        // tools/iqsrun's per-launch file (IQS_UID_FILE, mkstemp name) carries no history: any complete id is good
+        have = complete && (getenv("IQS_UID_FILE") != nullptr || (stamped && (long long)time(nullptr) - stamp <= kMaxAgeSeconds));
+      }
+      if (!have) std::this_thread::sleep_for(std::chrono::milliseconds(10));
+    }
+    if (!have) throw std::runtime_error("no fresh NCCL id in " + file + " after 60 s (is rank 0 running?)");
   }
   create_context(rank, used, uid, device);
   if (rank == 0 && !getenv("IQS_UID_FILE")) {

@@ -282,15 +282,11 @@ void QubitRegister<Type>::RestoreCanonicalPlacement() const {
   bool ranks_ok = true;
   for (unsigned g = M; g < n; ++g) ranks_ok = ranks_ok && where_[g] == g;
   if (!ranks_ok) {
-    const std::size_t myrank = (std::size_t)iqs::mpi::Environment::GetStateRank();
-    std::size_t destination = 0, source = 0;
-    for (unsigned g = M; g < n; ++g) {
-      // the content of rank bit g is position where_[g]: it belongs in rank bit where_[g]
-      if ((myrank >> (g - M)) & 1) destination |= std::size_t(1) << (where_[g] - M);
-      // my rank bit g must receive position g, which sits in rank bit place_[g]
-      if ((myrank >> (g - M)) & 1) source |= std::size_t(1) << (place_[g] - M);
-    }
-    Check(iqsb_permute_global(dev_, (int)source, (int)destination), "restoring the order of the global qubits");
+    // the content of rank bit g is position where_[g], which belongs in rank bit where_[g]; every
+    // rank derives its source, destination and the path from this table (no collective to agree)
+    std::vector<uint8_t> dst_rank_bit(n - M);
+    for (unsigned g = M; g < n; ++g) dst_rank_bit[g - M] = (uint8_t)(where_[g] - M);
+    Check(iqsb_permute_global_bits(dev_, dst_rank_bit.data(), n - M), "restoring the order of the global qubits");
     for (unsigned g = M; g < n; ++g) place_[g] = where_[g] = (uint8_t)g;
   }
   // 3. local bits: one bit permutation of the local index (in-place tile phases)

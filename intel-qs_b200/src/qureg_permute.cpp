@@ -1,123 +1,131 @@
 // qureg_permute.cpp -- reordering of the qubits (communication reduction).
 //
-// Reference behaviour restated: src/qureg_permute.cpp (PermuteQubits :10-41, EmulateSwap :45-52,
+// Reference behaviour: src/qureg_permute.cpp (PermuteQubits :10-41, EmulateSwap :45-52,
 // PermuteLocalQubits :55-104, PermuteGlobalQubits :108-187, PermuteByLocalGlobalExchangeOfQubitPairs
-// :191-229).  The per-amplitude host loop `state[p2d_new(d2p_old(i))] = old[i]` becomes one bit-
-// permutation kernel (csrc/kernels_misc.cu); the rank-to-rank block moves become peer-memory pulls
-// over NVLink (csrc/comm.cu).  All of it is pure data movement: bit-exact.
+// :191-229).  There every call moves the data at once: a host loop over all amplitudes into a second
+// copy of the state, a Sendrecv loop between ranks, one distributed ApplySwap per local/global pair.
+//
+// Here a permutation is first of all a RELABELLING.  The register already separates the position a
+// program qubit has in the reference's layout (qubit_permutation) from the physical bit that holds
+// that position (place_, src/placement.cpp), so PermuteQubits only has to say "position new_map[q] is
+// held by whatever bit held q's old position".  The data is brought into the reference's order by the
+// one routine that knows how to do that in few passes (RestoreCanonicalPlacement: up to three
+// local<->global pairs per NVLink pass, one whole-shard move for the rank bits, one in-place tiled
+// bit permutation for the local bits) --
+//   * at once when the register lives on one GPU (its `state` pointer is host-visible and the
+//     reference's tests read it right after the call), and
+//   * lazily when it is sharded: gates keep running on physical bits, a qubit the program moved to a
+//     "local" position is swapped in by the placement layer when a gate first needs it, and the order
+//     is restored before anything reads amplitudes by index.
+// All of it is pure data movement: bit-exact.
 #include "qureg_impl.hpp"
 
 namespace iqs {
 
 using detail::Check;
 
+// Program qubit q is from now on said to live at data position target.map[q]; no amplitude moves.
+template <class Type>
+void QubitRegister<Type>::Relabel(const Permutation &target) {
+  FlushForRead();  // queued gates were resolved against the old map
+  const unsigned n = (unsigned)num_qubits;
+  std::vector<uint8_t> holder(n);
+  std::vector<uint64_t> used(n);
+  for (unsigned q = 0; q < n; ++q) {
+    const unsigned was = (unsigned)qubit_permutation->map[q], is = (unsigned)target.map[q];
+    holder[is] = place_[was];
+    used[is] = last_use_[was];
+  }
+  bool identity = true;
+  for (unsigned p = 0; p < n; ++p) {
+    place_[p] = holder[p];
+    where_[holder[p]] = (uint8_t)p;
+    identity = identity && holder[p] == p;
+  }
+  last_use_ = used;
+  moved_ = !identity;
+  *qubit_permutation = target;
+}
+
+// after a relabelling: one GPU -> the data follows now; several -> when somebody needs the order
+template <class Type>
+void QubitRegister<Type>::SettleAfterRelabel() {
+  if (!placement_) RestoreCanonicalPlacement();
+}
+
 template <class Type>
 void QubitRegister<Type>::PermuteQubits(std::vector<std::size_t> new_map, std::string style_of_map) {
   assert(num_qubits == new_map.size());
-  unsigned nprocs = iqs::mpi::Environment::GetStateSize();
-  if (nprocs == 1) {
-    this->PermuteLocalQubits(new_map, style_of_map);
-  } else {
-    Permutation &qubit_permutation_old = *qubit_permutation;
-    Permutation qubit_permutation_new(new_map, style_of_map);
-    std::size_t M = LocalQubits();
-    std::vector<std::size_t> int_1_imap, int_2_imap;
-    qubit_permutation_old.ObtainIntemediateInverseMaps(qubit_permutation_new.map, M, int_1_imap, int_2_imap);
-    // local reshuffle, global reshuffle, then pairwise local<->global exchanges
-    this->PermuteLocalQubits(int_1_imap, "inverse");
-    this->PermuteGlobalQubits(int_2_imap, "inverse");
-    this->PermuteByLocalGlobalExchangeOfQubitPairs(new_map, style_of_map);
-  }
+  Permutation target(new_map, style_of_map);
+  if (target.map == qubit_permutation->map) return;
+  Relabel(target);
+  SettleAfterRelabel();
 }
 
 template <class Type>
 void QubitRegister<Type>::EmulateSwap(unsigned qubit_1, unsigned qubit_2) {
   assert(qubit_1 < num_qubits);
   assert(qubit_2 < num_qubits);
+  // the two qubits trade their roles, the amplitudes stay (queued gates hold positions, not qubits)
   qubit_permutation->ExchangeTwoElements(qubit_1, qubit_2);
 }
 
+// The three partial permutations of the reference's API.  Each checks what the reference asserts
+// about its argument and is then the same relabelling.
 template <class Type>
 void QubitRegister<Type>::PermuteLocalQubits(std::vector<std::size_t> new_map, std::string style_of_map) {
   assert(new_map.size() == this->num_qubits);
-  Permutation &old_qubit_permutation = *qubit_permutation;
-  Permutation new_qubit_permutation(new_map, style_of_map);
-  std::vector<std::size_t> &new_inverse_map = new_qubit_permutation.imap;
-  std::vector<std::size_t> &old_inverse_map = qubit_permutation->imap;
-  std::size_t M = LocalQubits();
-  // the new map must keep every local qubit local and leave the global positions alone
-  std::vector<bool> local(new_inverse_map.size(), 0);
-  for (unsigned pos = 0; pos < M; ++pos) local[new_inverse_map[pos]] = 1;
-  for (unsigned pos = 0; pos < M; ++pos) assert(local[old_inverse_map[pos]] > 0);
-  for (unsigned pos = M; pos < num_qubits; ++pos) assert(old_inverse_map[pos] == new_inverse_map[pos]);
-  if (old_inverse_map == new_inverse_map) return;
-
-  FlushForRead();
-  RestoreCanonicalPlacement();
-  BeforeDeviceOp();
-  // amplitude i (old data index) moves to program2data_new(data2program_old(i)): bit `pos` of i
-  // belongs to qubit old_imap[pos] and lands on position new_map[that qubit]
-  std::vector<uint8_t> dst_bit(M);
-  for (unsigned pos = 0; pos < M; ++pos) dst_bit[pos] = (uint8_t)new_qubit_permutation.map[old_inverse_map[pos]];
-  Check(iqsb_permute_local(dev_, dst_bit.data(), (unsigned)M), "PermuteLocalQubits");
-  old_qubit_permutation = new_qubit_permutation;
+  Permutation target(new_map, style_of_map);
+  const std::size_t M = LocalQubits();
+  for (std::size_t q = 0; q < num_qubits; ++q) {
+    const std::size_t was = qubit_permutation->map[q], is = target.map[q];
+    // a local qubit stays local, a global one stays exactly where it is
+    assert(was < M ? is < M : is == was);
+    (void)was;
+    (void)is;
+  }
+  (void)M;
+  if (target.map == qubit_permutation->map) return;
+  Relabel(target);
+  SettleAfterRelabel();
 }
 
 template <class Type>
 void QubitRegister<Type>::PermuteGlobalQubits(std::vector<std::size_t> new_map, std::string style_of_map) {
   assert(new_map.size() == this->num_qubits);
-  Permutation new_qubit_permutation(new_map, style_of_map);
-  std::vector<std::size_t> new_direct_map = new_qubit_permutation.map;
-  std::vector<std::size_t> new_inverse_map = new_qubit_permutation.imap;
-  std::vector<std::size_t> old_direct_map = qubit_permutation->map;
-  std::vector<std::size_t> old_inverse_map = qubit_permutation->imap;
-  std::size_t M = LocalQubits();
-  std::vector<bool> global(new_inverse_map.size(), 0);
-  for (unsigned pos = M; pos < num_qubits; ++pos) global[new_inverse_map[pos]] = 1;
-  for (unsigned pos = M; pos < num_qubits; ++pos) assert(global[old_inverse_map[pos]] > 0);
-  for (unsigned pos = 0; pos < M; ++pos) assert(old_inverse_map[pos] == new_inverse_map[pos]);
-  if (old_inverse_map == new_inverse_map) return;
-  assert(iqs::mpi::Environment::GetStateSize() > 1);
-
-  // this rank's shard goes to `destination` and is replaced by `source`'s (permute.cpp:149-166)
-  std::size_t myrank = iqs::mpi::Environment::GetStateRank();
-  std::size_t source = 0, destination = 0;
-  std::size_t glb_start = UL(myrank) * LocalSize();
-  for (unsigned pos = M; pos < num_qubits; ++pos) {
-    if (check_bit(glb_start, pos) == 1) {
-      destination += UL(1) << (new_direct_map[old_inverse_map[pos]] - M);
-      source += UL(1) << (old_direct_map[new_inverse_map[pos]] - M);
-    }
+  Permutation target(new_map, style_of_map);
+  const std::size_t M = LocalQubits();
+  for (std::size_t q = 0; q < num_qubits; ++q) {
+    const std::size_t was = qubit_permutation->map[q], is = target.map[q];
+    // a global qubit stays global, a local one stays exactly where it is
+    assert(was >= M ? is >= M : is == was);
+    (void)was;
+    (void)is;
   }
-  FlushForRead();
-  RestoreCanonicalPlacement();
-  BeforeDeviceOp();
-  Check(iqsb_permute_global(dev_, (int)source, (int)destination), "PermuteGlobalQubits");
-  qubit_permutation->SetNewPermutationFromMap(new_map, style_of_map);
+  (void)M;
+  if (target.map == qubit_permutation->map) return;
+  assert(iqs::mpi::Environment::GetStateSize() > 1);
+  Relabel(target);
+  SettleAfterRelabel();
 }
 
 template <class Type>
 void QubitRegister<Type>::PermuteByLocalGlobalExchangeOfQubitPairs(std::vector<std::size_t> new_map, std::string style_of_map) {
-  Permutation new_qubit_permutation(new_map, style_of_map);
-  std::vector<unsigned> exchanged_qubits(num_qubits, 0);
-  unsigned num_pairs = 0;
-  std::size_t M = LocalQubits();
-  for (unsigned qubit = 0; qubit < num_qubits; ++qubit) {
-    if (exchanged_qubits[qubit] != 0) continue;
-    unsigned old_position = (*qubit_permutation)[qubit];
-    unsigned new_position = new_qubit_permutation[qubit];
-    if (new_position == old_position) continue;
-    // the partner must form a 2-cycle with this qubit, one local and one global
-    unsigned partner_qubit = (unsigned)qubit_permutation->Find(new_position);
-    assert(exchanged_qubits[partner_qubit] == 0);
-    assert(new_qubit_permutation[partner_qubit] == old_position);
-    assert((old_position < M) != (new_position < M));
-    (void)M;
-    ApplySwap(qubit, partner_qubit);  // moves the data
-    qubit_permutation->ExchangeTwoElements(qubit, partner_qubit);
-    ++num_pairs;
-    exchanged_qubits[qubit] = exchanged_qubits[partner_qubit] = num_pairs;
+  Permutation target(new_map, style_of_map);
+  const std::size_t M = LocalQubits();
+  for (std::size_t q = 0; q < num_qubits; ++q) {
+    const std::size_t was = qubit_permutation->map[q], is = target.map[q];
+    if (was == is) continue;
+    // the qubit trades places with exactly one partner, across the local / global border
+    const std::size_t partner = qubit_permutation->Find(is);
+    assert(target.map[partner] == was);
+    assert((was < M) != (is < M));
+    (void)partner;
   }
+  (void)M;
+  if (target.map == qubit_permutation->map) return;
+  Relabel(target);  // the pairs travel together, up to three per pass (the reference: one ApplySwap each)
+  SettleAfterRelabel();
 }
 
 template class QubitRegister<ComplexSP>;

@@ -401,6 +401,25 @@ def test_small_fused_tiles(gpu_ctx, oracle):
         st.free()
 
 
+def test_one_amplitude_registers(gpu_ctx):
+    """The reference's default-constructed register holds ONE amplitude (qureg_init.cpp:22-52) and its
+    ==, ComputeOverlap, MaxAbsDiff and AmplitudeWiseSum work on it."""
+    a, b = gpu_ctx.alloc(1), gpu_ctx.alloc(1)
+    a.set_amp(0, 0.6 + 0.8j)
+    b.set_amp(0, 0.6 + 0.8j)
+    assert a.equal(b)
+    assert abs(a.overlap(b) - 1.0) < 1e-15
+    b.set_amp(0, 1.0)
+    assert not a.equal(b)
+    assert abs(a.overlap(b) - np.conj(1.0) * (0.6 + 0.8j)) < 1e-15
+    assert abs(a.maxabsdiff(b) - abs(0.6 + 0.8j - 1.0)) < 1e-15
+    assert abs(a.l2diff(b) - abs(0.6 + 0.8j - 1.0) ** 2) < 1e-15
+    a.axpy(b, 0.5j)
+    assert abs(a.get_amp(0) - (0.6 + 0.8j + 0.5j)) < 1e-15
+    a.free()
+    b.free()
+
+
 def _pauli_expect_numpy(psi, n, xmask, ymask, zmask):
     """<psi|P|psi> from the definition: P|i> = i^ny (-1)^popcount(i & (y|z)) |i ^ (x|y)>"""
     idx = np.arange(1 << n, dtype=np.uint64)

@@ -214,3 +214,15 @@ def test_closed_form_amplitudes_sharded(oracle, nranks, n, fused):
     assert sc.size == 2 * len(samples)
     err, scale = cf.check(samples, sc[0::2] + 1j * sc[1::2], TOL)
     print(f"closed form {n} qubits on {nranks} GPUs fused={fused}: {len(samples)} amplitudes, max |d| = {err:.3e} (largest |amp| {scale:.3e}), {got['seconds']:.2f} s")
+
+
+def test_barrier_gives_up_instead_of_hanging():
+    """One rank never reaches the rendezvous: the other gets IQSB_ERR_PEER after the deadline
+    (IQS_B200_BARRIER_TIMEOUT_S) -- the kernel does not spin for ever."""
+    need(2)
+    import subprocess
+
+    script = os.path.join(ROOT, "tests", "barrier_timeout_check.py")
+    r = subprocess.run([sys.executable, IQSRUN, "-n", "2", "--timeout", "120", sys.executable, script], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "TIMEOUT_OK" in r.stdout

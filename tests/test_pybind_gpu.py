@@ -259,3 +259,53 @@ def test_chi_matrix_binding_and_channels(iqs):
     psi.ApplyChannel(0, 3, chi2)
     ideal.ApplyCPauliZ(0, 3)
     assert abs(abs(ideal.ComputeOverlap(psi)) ** 2 - 1) < 1e-12
+
+
+def test_reference_binding_source_compiled_unchanged():
+    """The f1 drop-in proof: the reference's pybind11/intelqs_py.cpp, compiled UNCHANGED against
+    intel-qs_b200/include + libiqs.so (oracle/Makefile, target _ref/dropin/pybind), runs the reference's
+    unit_test/import_iqs.py scenario and the README circuit; the amplitudes equal the ones of the
+    engine's own module.  (Separate process: both modules are called intelqs_py.)"""
+    import glob
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    moddir = os.path.join(root, "oracle", "_ref", "dropin", "pybind")
+    assert glob.glob(os.path.join(moddir, "intelqs_py*.so")), "oracle/_ref/dropin/pybind is missing: run __graft_entry__.build() where /root/reference exists"
+    script = r"""
+import sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import intelqs_py as iqs
+assert iqs.__file__.startswith(sys.argv[1])
+iqs.EnvInit()
+rank = iqs.MPIEnvironment.GetRank()
+psi = iqs.QubitRegister(2, "base", 0, 0)   # unit_test/import_iqs.py
+print("The IQS library was successfully imported and initialized.")
+n = 6
+psi = iqs.QubitRegister(n, "base", 1, 0)
+for q in range(n):
+    psi.ApplyHadamard(q)
+psi.ApplyCPauliX(0, 3)
+psi.ApplyRotationY(2, 0.37)
+psi.ApplyToffoli(1, 2, 4)
+G = np.zeros((2, 2), dtype=np.complex128)
+G[0, 0], G[0, 1], G[1, 0], G[1, 1] = 0.5922 + 0.4596j, -0.0387 - 0.6608j, -0.1305 + 0.6490j, 0.4966 + 0.5621j
+psi.Apply1QubitGate(5, G)
+p = psi.GetProbability(4)
+amps = np.array([psi[i] for i in range(1 << n)])
+np.save(sys.argv[2], np.concatenate([amps, [p]]))
+iqs.EnvFinalize()
+"""
+    import tempfile
+
+    outs = []
+    with tempfile.TemporaryDirectory() as td:
+        for k, d in enumerate((moddir, os.path.join(root, "intel-qs_b200", "lib"))):
+            out = os.path.join(td, f"o{k}.npy")
+            r = subprocess.run([sys.executable, "-c", script, d, out], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+            assert "successfully imported" in r.stdout
+            outs.append(np.load(out))
+    assert np.array_equal(outs[0], outs[1])
+    assert abs(np.sum(np.abs(outs[0][:-1]) ** 2) - 1.0) < 0.05  # (the 4-digit matrix above is unitary to 1e-2 only)

@@ -130,6 +130,101 @@ __global__ void __launch_bounds__(kPermThreads) k_permute_tile(Cx<T> *__restrict
   }
 }
 
+// ---- the same phase with the global side on the bulk-copy engine ------------------------------
+// A tile is 2^(nS - kRun) runs of 2^kRun contiguous amplitudes (256 bytes of ComplexDP).  Each run
+// is one cp.async.bulk (UBLKCP) from global into shared memory, completion counted in bytes on an
+// mbarrier, and one cp.async.bulk back after the permutation -- no thread holds a global address
+// or a staging register for the copy, and the permutation inside the tile goes through registers
+// in place (8 amplitudes per thread, read before the barrier, written to their new slots after).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+
+constexpr int kBulkThreads = 512;
+template <typename T>
+__global__ void __launch_bounds__(kBulkThreads) k_permute_tile_bulk(Cx<T> *__restrict__ state, uint64_t nouter, TilePhase ph) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Cx<T> *tile = reinterpret_cast<Cx<T> *>(smem_raw);
+  __shared__ uint64_t g_run[256];  // offset (amplitudes) of run r inside the tile's footprint
+  __shared__ uint16_t l_lo[256], l_hi[16];
+  __shared__ __align__(8) uint64_t bar;
+  const int nS = ph.nS;  // >= kRun, pos[0..kRun) == 0..kRun-1
+  const unsigned nruns = 1u << (nS - kRun), tsize = 1u << nS;
+  constexpr unsigned kRunBytes = (unsigned)sizeof(Cx<T>) << kRun;
+  for (unsigned t = threadIdx.x; t < 256 + 16; t += kBulkThreads) {
+    unsigned v = t < 256 ? t : (t - 256) << 8;
+    unsigned lo = 0;
+    for (int k = 0; k < nS; ++k)
+      if ((v >> k) & 1u) lo |= 1u << ph.dstslot[k];
+    if (t < 256) l_lo[t] = (uint16_t)lo;
+    else l_hi[t - 256] = (uint16_t)lo;
+    if (t < 256) {
+      uint64_t go = 0;
+      for (int k = kRun; k < nS; ++k)
+        if ((t >> (k - kRun)) & 1u) go |= 1ull << ph.pos[k];
+      g_run[t] = go;
+    }
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  unsigned parity = 0;
+  constexpr int U = 4096 / kBulkThreads;
+  for (uint64_t o = blockIdx.x; o < nouter; o += gridDim.x, parity ^= 1u) {
+    uint64_t base = o;
+    for (int k = 0; k < nS; ++k) base = insert_zero(base, ph.pos[k]);
+    // a bulk copy is one warp-level instruction with uniform operands (UBLKCP): lane 0 of every warp
+    // issues its share of the runs, so the 16 warps feed the copy engine side by side.  (The byte
+    // count may be credited before or after the barrier is armed: the count is signed.)
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, tsize * (unsigned)sizeof(Cx<T>));
+    if ((threadIdx.x & 31) == 0)
+      for (unsigned r = threadIdx.x >> 5; r < nruns; r += kBulkThreads / 32) bulk_g2s(tile + ((size_t)r << kRun), state + (base | g_run[r]), kRunBytes, &bar);
+    mbar_wait(&bar, parity);
+    Cx<T> v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned t = threadIdx.x + u * kBulkThreads;
+      if (t < tsize) v[u] = tile[t];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned t = threadIdx.x + u * kBulkThreads;
+      if (t < tsize) tile[l_lo[t & 255] | l_hi[t >> 8]] = v[u];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      for (unsigned r = threadIdx.x >> 5; r < nruns; r += kBulkThreads / 32) bulk_s2g(state + (base | g_run[r]), tile + ((size_t)r << kRun), kRunBytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile may be overwritten
+    }
+    __syncthreads();
+  }
+}
+
 // Split "content of position b goes to position dst[b]" into tile phases.
 static int plan_phases(const uint8_t *dst, unsigned nbits, TilePhase *out, int max_phases) {
   uint8_t cur[64];
@@ -300,6 +395,12 @@ extern "C" int iqsb_permute_local(iqsb_state *st, const uint8_t *dst_bit, unsign
     threads = e ? atoi(e) : 512;
     if (threads != 256 && threads != 512 && threads != 1024) threads = 512;
   }
+  // IQS_B200_PERMUTE_BULK=1 moves full tiles with the bulk-copy engine (k_permute_tile_bulk).  Measured at 32
+  // qubits (profiles/r02o_permute_bulk_n32.log): 27.2 ms per phase against 25.0 ms for the per-thread
+  // 16-byte accesses -- a tile built from arbitrary positions only offers 256-byte runs, too short for
+  // the engine, and the register pass needs 2 CTAs of 512 threads per SM -- so it stays opt-in.
+  const char *be = getenv("IQS_B200_PERMUTE_BULK");
+  const bool use_bulk = be && *be == '1';
   for (int p = 0; p < nph; ++p) {
     const TilePhase &ph = phases[p];
     size_t smem = st->amp_bytes() << ph.nS;
@@ -314,13 +415,29 @@ extern "C" int iqsb_permute_local(iqsb_state *st, const uint8_t *dst_bit, unsign
     unsigned grid = (unsigned)(nouter < cap ? nouter : cap);                                                           \
     k_permute_tile<T, TH><<<grid, TH, smem, ctx->stream>>>((Cx<T> *)st->d, nouter, ph);                                \
   }
-    if (st->dtype == IQSB_F64) {
+#define IQSB_PERM_BULK(T)                                                                                              \
+  {                                                                                                                    \
+    int per_sm = 1;                                                                                                    \
+    IQSB_CUDA(cudaFuncSetAttribute(k_permute_tile_bulk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    IQSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_permute_tile_bulk<T>, kBulkThreads, smem));     \
+    if (per_sm < 1) per_sm = 1;                                                                                        \
+    uint64_t cap = (uint64_t)ctx->num_sms * per_sm;                                                                    \
+    unsigned grid = (unsigned)(nouter < cap ? nouter : cap);                                                           \
+    k_permute_tile_bulk<T><<<grid, kBulkThreads, smem, ctx->stream>>>((Cx<T> *)st->d, nouter, ph);                      \
+  }
+    // full-size tiles whose lowest kRun slots are the lowest kRun positions move through the bulk-copy engine
+    bool bulk = use_bulk && ph.nS == kTileMax;
+    for (int k = 0; k < kRun && bulk; ++k) bulk = ph.pos[k] == k;
+    if (bulk) {
+      if (st->dtype == IQSB_F64) IQSB_PERM_BULK(double) else IQSB_PERM_BULK(float)
+    } else if (st->dtype == IQSB_F64) {
       if (threads == 256) IQSB_PERM_LAUNCH(double, 256) else if (threads == 1024) IQSB_PERM_LAUNCH(double, 1024) else IQSB_PERM_LAUNCH(double, 512)
     } else {
       if (threads == 256) IQSB_PERM_LAUNCH(float, 256) else if (threads == 1024) IQSB_PERM_LAUNCH(float, 1024) else IQSB_PERM_LAUNCH(float, 512)
     }
 #undef IQSB_PERM_LAUNCH
-    IQSB_TRY(iqsb_check_launch(ctx, "k_permute_tile"));
+#undef IQSB_PERM_BULK
+    IQSB_TRY(iqsb_check_launch(ctx, bulk ? "k_permute_tile_bulk" : "k_permute_tile", 2.0 * (double)st->local_amps * st->amp_bytes()));
   }
   return IQSB_OK;
 }

@@ -312,6 +312,29 @@ def test_permute_local_bit_exact(gpu_ctx):
     st.free()
 
 
+def test_permute_local_on_the_bulk_copy_engine(gpu_ctx, monkeypatch):
+    """IQS_B200_PERMUTE_BULK=1: tiles travel as 256-byte cp.async.bulk runs with an mbarrier (opt-in,
+    measured slower than the default for these short runs); the result is the same, bit for bit."""
+    import os
+
+    n = 18
+    st = gpu_ctx.alloc(1 << n)
+    psi = C.random_state(n, seed=80)
+    rng = np.random.default_rng(5)
+    idx = np.arange(1 << n, dtype=np.uint64)
+    monkeypatch.setenv("IQS_B200_PERMUTE_BULK", "1")
+    for dst in [list(rng.permutation(n)) for _ in range(3)] + [list(range(n))[::-1]]:
+        st.upload(psi)
+        st.permute_local(dst)
+        j = np.zeros_like(idx)
+        for b in range(n):
+            j |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(dst[b])
+        want = np.empty_like(psi)
+        want[j] = psi
+        assert np.array_equal(st.download(), want)
+    st.free()
+
+
 def test_fused_matches_sequential(gpu_ctx, oracle):
     """Targets and controls anywhere: the batch is cut into tile runs, the result equals the
     gate-by-gate oracle bit for bit."""

@@ -84,6 +84,11 @@ def main():
     if "prob" in ops:
         for pos in (0, 1, 10, n - 1):
             timeit("prob1", pos, lambda pos=pos: st.prob1(pos), 8.0 * L)
+    if "prob" in ops:
+        timeit("prob_all", "-", lambda: st.prob_all(), 16.0 * L)
+    if "pauli" in ops or "parity" in ops:
+        for name, (xm, ym, zm) in (("X0", (1, 0, 0)), ("X5Y9Z1", (1 << 5, 1 << 9, 2)), ("XtopY0", (1 << (n - 1), 1, 0)), ("X0..3", (15, 0, 0))):
+            timeit("pauli", name, lambda xm=xm, ym=ym, zm=zm: st.pauli_expect(xm, ym, zm), 16.0 * L)
     if "norm" in ops:
         timeit("norm2", "-", lambda: st.norm2(), 16.0 * L)
     if "parity" in ops:

@@ -54,7 +54,10 @@ namespace {
 #ifndef IQSB_FUSED_REGBITS
 #define IQSB_FUSED_REGBITS 3
 #endif
-constexpr int kThreads = 256;
+#ifndef IQSB_FUSED_THREADS
+#define IQSB_FUSED_THREADS 256
+#endif
+constexpr int kThreads = IQSB_FUSED_THREADS;
 constexpr int kMaxFusedGates = 4096;
 constexpr int kTile = IQSB_FUSED_TILE;  // tile exponent (<= 12)
 // (A variant with two tile buffers of 2^11 amplitudes per CTA, the next tile fetched while the current

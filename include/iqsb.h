@@ -183,6 +183,20 @@ int iqsb_plan_fused(const iqsb_fgate *gates, int ngates, unsigned log2_local, in
 int iqsb_plan_fused_order(const iqsb_fgate *gates, int ngates, unsigned log2_local, int reorder, int *order, int *run_end, uint8_t *tiles,
                           int max_runs, int *nruns);
 
+/* Pure host function: the complete schedule of iqsb_fused for a ComplexDP register, decoded from the
+ * descriptors the kernel reads.  out[k] = the k-th gate executed: its index in gates[], its run, its
+ * group (numbered over all runs), its arithmetic class (0 general, 1 real, 2 diagonal, 3 diag(1,d),
+ * 4 anti-diagonal, 5 exact X, 6 real diagonal + imaginary off-diagonal, 7 sqrt X, 8 sqrt Y), the
+ * register bit of its target and the kind of its control (0 none, 1 register bit, 2 thread bit,
+ * 3 bit of the tile's base index).  group_pos[4 g + j] = position held by register bit j of group g
+ * (255 = unused); group_pos holds 4 bytes per gate at most. */
+typedef struct iqsb_fused_trace {
+  int32_t gate, run, group;
+  uint8_t cls, tbit, ckind, c;
+} iqsb_fused_trace;
+int iqsb_plan_fused_trace(const iqsb_fgate *gates, int ngates, unsigned log2_local, int reorder, iqsb_fused_trace *out, uint8_t *group_pos,
+                          int *ngroups);
+
 /* ---- reductions (warp-shuffle + fixed-order second stage; deterministic run to run) -- */
 /* sum |a|^2 over local amplitudes with bit pos == 1: GetProbability (src/qureg_measure.cpp:150-167) */
 int iqsb_prob1(iqsb_state *st, unsigned pos, double *out);

@@ -120,6 +120,24 @@ def plan_fused_order(gates, log2_local, reorder=True):
     return out
 
 
+class FusedTrace(ctypes.Structure):
+    _fields_ = [("gate", ctypes.c_int32), ("run", ctypes.c_int32), ("group", ctypes.c_int32),
+                ("cls", ctypes.c_uint8), ("tbit", ctypes.c_uint8), ("ckind", ctypes.c_uint8), ("c", ctypes.c_uint8)]
+
+
+def plan_fused_trace(gates, log2_local, reorder=True):
+    """Host-only: (list of dicts, one per gate in execution order; list of register positions per group)."""
+    arr = _fgates(gates)
+    n = len(gates)
+    out = (FusedTrace * max(n, 1))()
+    gpos = np.zeros(4 * max(n, 1), dtype=np.uint8)
+    ng = c_int()
+    _chk(load().iqsb_plan_fused_trace(arr, n, log2_local, int(bool(reorder)), out, gpos.ctypes.data_as(c_vp), ctypes.byref(ng)))
+    trace = [dict(gate=out[k].gate, run=out[k].run, group=out[k].group, cls=out[k].cls, tbit=out[k].tbit, ckind=out[k].ckind, c=out[k].c) for k in range(n)]
+    groups = [[int(p) for p in gpos[4 * g : 4 * g + 4] if p != 255] for g in range(ng.value)]
+    return trace, groups
+
+
 def plan_permute(dst_bit):
     """Host-only: list of (positions, dstslot) tile phases for a local qubit permutation."""
     a = np.ascontiguousarray(dst_bit, dtype=np.uint8)
@@ -186,6 +204,7 @@ def load():
         "iqsb_fused_max_log2tile": [c_vp],
         "iqsb_plan_fused": [c_vp, c_int, c_uint, c_vp, c_vp, c_int, ctypes.POINTER(c_int)],
         "iqsb_plan_fused_order": [c_vp, c_int, c_uint, c_int, c_vp, c_vp, c_vp, c_int, ctypes.POINTER(c_int)],
+        "iqsb_plan_fused_trace": [c_vp, c_int, c_uint, c_int, c_vp, c_vp, ctypes.POINTER(c_int)],
         "iqsb_prob1": [c_vp, c_uint, ctypes.POINTER(c_dbl)],
         "iqsb_parity_expect": [c_vp, c_u64, c_u64, ctypes.POINTER(c_dbl)],
         "iqsb_norm2": [c_vp, ctypes.POINTER(c_dbl)],

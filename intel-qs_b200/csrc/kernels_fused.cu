@@ -73,7 +73,7 @@ constexpr int kBatchGroups = 24;
 constexpr int kReorderWindow = 512;     // how far the planner looks past the first skipped gate
 static_assert(kTile >= 9 && kTile <= 12, "tile geometry");
 
-enum GateClass : uint8_t { kGeneral = 0, kReal, kDiag, kDiag1, kAnti, kXExact, kRealDiagImagOff };
+enum GateClass : uint8_t { kGeneral = 0, kReal, kDiag, kDiag1, kAnti, kXExact, kRealDiagImagOff, kSqrtX, kSqrtY };
 
 template <typename T>
 struct alignas(16) FGate {
@@ -85,7 +85,8 @@ struct alignas(16) FGate {
   uint8_t en;     // mask of the kAmps/2 register pairs the gate acts on
   uint8_t last;   // 1: last gate of its group
   uint8_t pad8[2];
-  uint32_t pad32[2];
+  uint32_t origin;  // index of the gate in the caller's list (iqsb_plan_fused_trace)
+  uint32_t pad32;
 };
 
 struct alignas(16) GroupDesc {
@@ -178,6 +179,14 @@ __device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Ma
   switch (cls) {
     case kXExact:  // out0 = in1, out1 = in0.  The only class that takes a control among the register bits
                    // (`en` = the pairs whose control bit is set): CNOTs are moves between registers.
+      if (en == (1u << (kAmps / 2)) - 1u) {  // plain X: every pair trades places
+        for_pairs<T, B>(a, [&](Cx<T> &x, Cx<T> &y) {
+          const Cx<T> t = x;
+          x = y;
+          y = t;
+        });
+        break;
+      }
 #pragma unroll
       for (int k = 0; k < kAmps / 2; ++k) {
         const int r0 = ((k >> B) << (B + 1)) | (k & ((1 << B) - 1));
@@ -245,6 +254,32 @@ __device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Ma
           o0.im = add_rn(mul_rn(r00, x.im), mul_rn(i01, y.re));
           o1.re = add_rn(-mul_rn(i10, x.im), mul_rn(r11, y.re));
           o1.im = add_rn(mul_rn(i10, x.re), mul_rn(r11, y.im));
+        }
+        x = o0;
+        y = o1;
+      });
+      break;
+    }
+    case kSqrtX:
+    case kSqrtY: {
+      // every entry is +-1/2 +- i/2 (reference src/qureg_apply1qubitgate.cpp:389-431).  A product with 1/2 is
+      // exact and fl(a/2 - b/2) = fl(a - b)/2, so the reference's 28 operations collapse to 4 sums of the
+      // inputs, 4 sums of those and 4 halvings -- the same values unless an intermediate is subnormal.
+      const bool sx = cls == kSqrtX;
+      for_pairs<T, B>(a, [&](Cx<T> &x, Cx<T> &y) {
+        const T A = sub_rn(x.re, x.im), Bp = add_rn(x.re, x.im), Cp = add_rn(y.re, y.im), D = sub_rn(y.re, y.im);
+        const T h = (T)0.5;
+        Cx<T> o0, o1;
+        if (sx) {  // 1/2 [[1+i, 1-i], [1-i, 1+i]]
+          o0.re = mul_rn(h, add_rn(A, Cp));
+          o0.im = mul_rn(h, sub_rn(Bp, D));
+          o1.re = mul_rn(h, add_rn(Bp, D));
+          o1.im = mul_rn(h, sub_rn(Cp, A));
+        } else {   // 1/2 [[1+i, -1-i], [1+i, 1+i]]
+          o0.re = mul_rn(h, sub_rn(A, D));
+          o0.im = mul_rn(h, sub_rn(Bp, Cp));
+          o1.re = mul_rn(h, add_rn(A, D));
+          o1.im = mul_rn(h, add_rn(Bp, Cp));
         }
         x = o0;
         y = o1;
@@ -399,6 +434,9 @@ uint8_t classify(const double m[8]) {
   if (z01 && z10) return (m[0] == 1. && m[1] == 0.) ? kDiag1 : kDiag;
   if (m[1] == 0. && m[3] == 0. && m[5] == 0. && m[7] == 0.) return kReal;
   if (m[1] == 0. && m[7] == 0. && m[2] == 0. && m[4] == 0.) return kRealDiagImagOff;
+  static const double sqrt_x[8] = {0.5, 0.5, 0.5, -0.5, 0.5, -0.5, 0.5, 0.5}, sqrt_y[8] = {0.5, 0.5, -0.5, -0.5, 0.5, 0.5, 0.5, 0.5};
+  if (memcmp(m, sqrt_x, sizeof(sqrt_x)) == 0) return kSqrtX;
+  if (memcmp(m, sqrt_y, sizeof(sqrt_y)) == 0) return kSqrtY;
   return kGeneral;
 }
 
@@ -547,6 +585,7 @@ void build_batches(const iqsb_fgate *in, const std::vector<int> &run, const Tile
       memset(&o, 0, sizeof(o));
       o.m = make_mat<T>(q.m);
       o.cls = classify(q.m);
+      o.origin = (uint32_t)run[k];
       const int ts = slot_of[q.target];
       for (int j = 0; j < kRegBits; ++j)
         if (hg.rs[j] == ts) o.tbit = (uint8_t)j;
@@ -720,6 +759,63 @@ extern "C" int iqsb_plan_fused_order(const iqsb_fgate *gates, int ngates, unsign
     IQSB_REQUIRE(gates[i].target >= 0 && gates[i].target < 64 && (gates[i].kind != 1 || (gates[i].control >= 0 && gates[i].control < 64)),
                  "iqsb_plan_fused_order: gate %d has a bad position", i);
   return plan_runs(gates, ngates, log2_local, reorder != 0, order, run_end, tiles, max_runs, nruns);
+}
+
+// Pure host function: the complete schedule iqsb_fused builds for a ComplexDP register -- runs, groups,
+// the arithmetic class and the kind of control of every gate -- decoded from the very descriptors the
+// kernel reads.  out[k] describes the k-th gate executed; group_pos[4 g + j] = the position held by
+// register bit j of group g (groups numbered over all runs).
+extern "C" int iqsb_plan_fused_trace(const iqsb_fgate *gates, int ngates, unsigned log2_local, int reorder, iqsb_fused_trace *out, uint8_t *group_pos,
+                                     int *ngroups) {
+  IQSB_REQUIRE((gates || ngates == 0) && out && group_pos && ngroups, "iqsb_plan_fused_trace: null argument");
+  IQSB_REQUIRE(log2_local >= (unsigned)kRegBits + 1, "iqsb_plan_fused_trace: shards below 2^%d amplitudes are not tiled", kRegBits + 1);
+  *ngroups = 0;
+  if (ngates == 0) return IQSB_OK;
+  for (int i = 0; i < ngates; ++i)
+    IQSB_REQUIRE((gates[i].kind == 0 || gates[i].kind == 1) && gates[i].target >= 0 && (unsigned)gates[i].target < log2_local &&
+                     (gates[i].kind == 0 || (gates[i].control >= 0 && (unsigned)gates[i].control < log2_local && gates[i].control != gates[i].target)),
+                 "iqsb_plan_fused_trace: gate %d is not a gate on local positions", i);
+  std::vector<int> order((size_t)ngates), run_end((size_t)ngates);
+  std::vector<uint8_t> tiles((size_t)ngates * 16);
+  int nruns = 0;
+  IQSB_TRY(plan_runs(gates, ngates, log2_local, reorder != 0, order.data(), run_end.data(), tiles.data(), ngates, &nruns));
+  int first = 0, k = 0, g = 0;
+  for (int r = 0; r < nruns; ++r) {
+    TileDesc td;
+    td.nS = tiles[r * 16];
+    for (int j = 0; j < kTile; ++j) td.pos[j] = tiles[r * 16 + 1 + j];
+    std::vector<int> run(order.begin() + first, order.begin() + run_end[r]);
+    first = run_end[r];
+    std::vector<unsigned char> blob;
+    int nbatches = 0;
+    build_batches<double>(gates, run, td, reorder != 0, blob, nbatches);
+    for (int b = 0; b < nbatches; ++b) {
+      const unsigned char *base = blob.data() + (size_t)b * batch_stride<double>();
+      const BatchHdr *h = reinterpret_cast<const BatchHdr *>(base);
+      const GroupDesc *gd = reinterpret_cast<const GroupDesc *>(base + sizeof(BatchHdr));
+      const FGate<double> *fg = reinterpret_cast<const FGate<double> *>(base + sizeof(BatchHdr) + kBatchGroups * sizeof(GroupDesc));
+      for (int gi = 0; gi < h->ngroups; ++gi, ++g) {
+        for (int j = 0; j < 4; ++j) group_pos[4 * g + j] = 255;
+        for (int j = 0; j < kRegBits; ++j) {
+          const unsigned one_hot = swz(gd[gi].p[j]);  // the swizzle is an involution
+          group_pos[4 * g + j] = td.pos[__builtin_ctz(one_hot)];
+        }
+        for (int q = gd[gi].gate_first; q < gd[gi].gate_first + gd[gi].gate_count; ++q, ++k) {
+          IQSB_REQUIRE(k < ngates, "iqsb_plan_fused_trace: internal error (more gates scheduled than given)");
+          out[k].gate = (int32_t)fg[q].origin;
+          out[k].run = r;
+          out[k].group = g;
+          out[k].cls = fg[q].cls;
+          out[k].tbit = fg[q].tbit;
+          out[k].ckind = fg[q].ckind;
+          out[k].c = fg[q].c;
+        }
+      }
+    }
+  }
+  IQSB_REQUIRE(k == ngates, "iqsb_plan_fused_trace: internal error (%d of %d gates scheduled)", k, ngates);
+  *ngroups = g;
+  return IQSB_OK;
 }
 
 extern "C" int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates) {

@@ -521,6 +521,7 @@ def _class_matrices():
         "anti": np.array([0, 0, 0, -1, 0, 1, 0, 0.0]),  # Y
         "x": X,
         "sqrtx": np.array([0.5, 0.5, 0.5, -0.5, 0.5, -0.5, 0.5, 0.5]),
+        "sqrty": np.array([0.5, 0.5, -0.5, -0.5, 0.5, 0.5, 0.5, 0.5]),
     }
 
 

@@ -113,3 +113,78 @@ def test_reordered_plans_respect_exact_commutation():
         plan = capi.plan_fused_order(gates, M)
         check_order(gates, plan, M)
         assert len(plan) <= len(capi.plan_fused(gates, M))
+
+
+# ---- the full schedule: runs -> groups (three register bits) -> gates with class and control kind ----
+G = np.array([0.5922, 0.4596, -0.0387, -0.6608, -0.1305, 0.6490, 0.4966, 0.5621])  # a general matrix
+T = np.array([1, 0, 0, 0, 0, 0, np.cos(np.pi / 4), np.sin(np.pi / 4)])
+SX = np.array([0.5, 0.5, 0.5, -0.5, 0.5, -0.5, 0.5, 0.5])
+CLS = {"general": 0, "real": 1, "diag": 2, "diag1": 3, "anti": 4, "x": 5, "rx": 6, "sqrtx": 7, "sqrty": 8}
+
+
+def check_trace(gates, M, reorder=True):
+    trace, groups = capi.plan_fused_trace(gates, M, reorder)
+    assert sorted(t["gate"] for t in trace) == list(range(len(gates)))
+    when = {t["gate"]: k for k, t in enumerate(trace)}
+    for a, b in zip(trace, trace[1:]):
+        assert (b["run"], b["group"]) >= (a["run"], a["group"])  # runs and groups are executed in order
+    for t in trace:
+        g = gates[t["gate"]]
+        regs = groups[t["group"]]
+        assert len(regs) == 3 and len(set(regs)) == 3
+        assert regs[t["tbit"]] == g[2]  # the target is the register bit the kernel is told
+        if g[0] == 1:
+            assert t["ckind"] in (1, 2, 3)
+            # only an exact X takes its control among the register bits (a move between registers);
+            # the arithmetic classes are straight-line code over all register pairs
+            if t["ckind"] == 1:
+                assert t["cls"] == CLS["x"] and regs[t["c"]] == g[1]
+            else:
+                assert g[1] not in regs
+        else:
+            assert t["ckind"] == 0
+    for i in range(len(gates)):
+        for j in range(i + 1, len(gates)):
+            if when[j] < when[i]:
+                assert not (_qubits(gates[i]) & _qubits(gates[j])), (i, j)
+                assert _is_perm(gates[i]) or _is_perm(gates[j]), (i, j)
+    return trace, groups
+
+
+def test_schedule_classes_and_controls():
+    gates = [(0, 0, 0, G), (0, 0, 1, H), (0, 0, 2, T), (0, 0, 3, SX), (1, 0, 1, X), (1, 2, 3, X), (1, 5, 4, G), (1, 4, 5, H), (0, 0, 6, X)]
+    trace, groups = check_trace(gates, 20)
+    cls = {t["gate"]: t["cls"] for t in trace}
+    assert [cls[i] for i in range(4)] == [CLS["general"], CLS["real"], CLS["diag1"], CLS["sqrtx"]]
+    assert cls[4] == CLS["x"] and cls[8] == CLS["x"]
+    kinds = {t["gate"]: t["ckind"] for t in trace}
+    assert kinds[4] == 1  # CNOT(0,1): both in the first group's registers
+    assert kinds[6] == 2 and kinds[7] == 2  # controlled arithmetic gates: control on a thread bit
+    # controlled-G(5 -> 4) and controlled-H(4 -> 5) cannot share a group: each one's control is the other's target
+    g_of = {t["gate"]: t["group"] for t in trace}
+    assert g_of[6] != g_of[7]
+
+
+def test_schedule_of_a_bench_layer_absorbs_the_cnots():
+    """32 one-qubit gates + 16 CNOTs: 4 runs; in the first run (qubits 0..11) the 6 CNOTs join the 4
+    groups of the one-qubit gates instead of opening their own."""
+    for parity in (0, 1):
+        gates = [(0, 0, q, (G, H, T, SX)[q % 4]) for q in range(32)] + [(1, q, q + 1, X) for q in range(parity, 31, 2)]
+        trace, groups = check_trace(gates, 32)
+        assert max(t["run"] for t in trace) == 3
+        first_run = [t for t in trace if t["run"] == 0]
+        assert len({t["group"] for t in first_run}) == 4
+        assert sum(1 for t in first_run if t["cls"] == CLS["x"]) >= 5
+        assert len(groups) <= 12
+
+
+def test_random_schedules():
+    rng = np.random.default_rng(23)
+    mats = [G, H, T, SX, X, X]
+    for M in (4, 6, 12, 13, 33):
+        gates = []
+        for i in range(180):
+            c, t = (int(x) for x in rng.permutation(M)[:2])
+            gates.append((int(rng.integers(0, 2)), c, t, mats[int(rng.integers(0, len(mats)))]))
+        check_trace(gates, M)
+        check_trace(gates, M, reorder=False)

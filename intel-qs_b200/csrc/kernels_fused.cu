@@ -298,7 +298,7 @@ __device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Ma
 template <typename T, bool FMA>
 __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
     k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, const unsigned char *__restrict__ desc, int nbatches,
-            unsigned long long *__restrict__ next_tile) {
+            unsigned long long *__restrict__ next_tile, int debug_no_io) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cx<T> *tile = reinterpret_cast<Cx<T> *>(smem_raw);
   // chunk offset of tile-local chunk index c = lo | hi << 8 (c = tile-local amplitude index / 2)
@@ -354,8 +354,10 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
     }
     __syncthreads();
     if (s_tile == ~0ull) break;
-    tile_load_async<T>(tile, state + (s_tile >> 1), g_lo, g_hi, nchunks);
-    cp_async_wait<0>();
+    if (!debug_no_io) {  // (IQS_B200_FUSED_DEBUG=noio times the tile phase alone: the state is not touched)
+      tile_load_async<T>(tile, state + (s_tile >> 1), g_lo, g_hi, nchunks);
+      cp_async_wait<0>();
+    }
     for (int b = 0; b < nbatches; ++b) {
       if (nbatches > 1) {
         if (b) __syncthreads();  // nobody still reads the previous batch
@@ -415,7 +417,8 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
       }
     }
     Chunk<T> *g = state + (s_tile >> 1);
-    if (nchunks % (kThreads * 2) == 0) tile_store<T, 2>(tile, g, g_lo, g_hi, nchunks);
+    if (debug_no_io) {
+    } else if (nchunks % (kThreads * 2) == 0) tile_store<T, 2>(tile, g, g_lo, g_hi, nchunks);
     else tile_store<T, 1>(tile, g, g_lo, g_hi, nchunks);
     __syncthreads();
   }
@@ -656,7 +659,9 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run
     counter = ctx->d_tile_counter;
     IQSB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
   }
-  kernel<<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, nbatches, counter);
+  const char *dbg = getenv("IQS_B200_FUSED_DEBUG");
+  const int no_io = dbg && strcmp(dbg, "noio") == 0;
+  kernel<<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, nbatches, counter, no_io);
   return iqsb_check_launch(ctx, "k_fused", 2.0 * (double)st->local_amps * st->amp_bytes());
 }
 

@@ -338,6 +338,10 @@ int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank);
  * dst_rank_bit[b], nbits = log2(nranks)): every rank derives its source, its destination and the
  * path all ranks take from the table -- no collective is needed to agree. */
 int iqsb_permute_global_bits(iqsb_state *st, const uint8_t *dst_rank_bit, unsigned nbits);
+/* Pure host function: the plan of iqsb_permute_global_bits for one rank -- the rank it pulls its new
+ * shard from, the rank its shard goes to, whether all ranks move in pairs, whether nothing moves. */
+int iqsb_plan_permute_global_bits(int rank, int nranks, const uint8_t *dst_rank_bit, unsigned nbits, int *source, int *destination, int *pairwise,
+                                  int *identity);
 /* bytes this context moved over NVLink (peer loads + peer stores) since creation. */
 uint64_t iqsb_nvlink_bytes(const iqsb_ctx *ctx);
 

@@ -138,6 +138,14 @@ def plan_fused_trace(gates, log2_local, reorder=True):
     return trace, groups
 
 
+def plan_permute_global_bits(rank, nranks, dst_rank_bit):
+    """Host-only: (source rank, destination rank, pairwise, identity) of a rank-bit permutation for `rank`."""
+    a = np.ascontiguousarray(dst_rank_bit, dtype=np.uint8)
+    src, dst, pw, ident = c_int(), c_int(), c_int(), c_int()
+    _chk(load().iqsb_plan_permute_global_bits(rank, nranks, a.ctypes.data_as(c_vp), a.size, ctypes.byref(src), ctypes.byref(dst), ctypes.byref(pw), ctypes.byref(ident)))
+    return src.value, dst.value, bool(pw.value), bool(ident.value)
+
+
 def plan_permute(dst_bit):
     """Host-only: list of (positions, dstslot) tile phases for a local qubit permutation."""
     a = np.ascontiguousarray(dst_bit, dtype=np.uint8)
@@ -204,6 +212,7 @@ def load():
         "iqsb_fused_max_log2tile": [c_vp],
         "iqsb_plan_fused": [c_vp, c_int, c_uint, c_vp, c_vp, c_int, ctypes.POINTER(c_int)],
         "iqsb_plan_fused_order": [c_vp, c_int, c_uint, c_int, c_vp, c_vp, c_vp, c_int, ctypes.POINTER(c_int)],
+        "iqsb_plan_permute_global_bits": [c_int, c_int, c_vp, c_uint, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
         "iqsb_plan_fused_trace": [c_vp, c_int, c_uint, c_int, c_vp, c_vp, ctypes.POINTER(c_int)],
         "iqsb_prob1": [c_vp, c_uint, ctypes.POINTER(c_dbl)],
         "iqsb_parity_expect": [c_vp, c_u64, c_u64, ctypes.POINTER(c_dbl)],

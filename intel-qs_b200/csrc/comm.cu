@@ -560,29 +560,41 @@ extern "C" int iqsb_permute_global(iqsb_state *st, int src_rank, int dst_rank) {
   return permute_global_impl(st, src_rank, dst_rank, -1);
 }
 
-// The content of rank bit b moves to rank bit dst_rank_bit[b].  Every rank derives its own source and
-// destination AND whether all ranks move in pairs (the bit permutation is an involution) from the same
-// table: nothing has to be agreed at run time.
-extern "C" int iqsb_permute_global_bits(iqsb_state *st, const uint8_t *dst_rank_bit, unsigned nbits) {
-  IQSB_REQUIRE(st && dst_rank_bit, "iqsb_permute_global_bits: null argument");
-  iqsb_ctx *ctx = st->ctx;
-  IQSB_REQUIRE(nbits < 31 && (1 << nbits) == ctx->nranks, "iqsb_permute_global_bits: %u rank bits do not describe %d ranks", nbits, ctx->nranks);
+// Pure host function (no GPU needed): what `rank` does when the content of rank bit b moves to rank bit
+// dst_rank_bit[b].  Every rank derives its own source and destination AND whether all ranks move in
+// pairs (the bit permutation is an involution) from the same table: nothing has to be agreed at run time.
+extern "C" int iqsb_plan_permute_global_bits(int rank, int nranks, const uint8_t *dst_rank_bit, unsigned nbits, int *source, int *destination,
+                                             int *pairwise, int *identity) {
+  IQSB_REQUIRE(dst_rank_bit && source && destination && pairwise && identity, "iqsb_plan_permute_global_bits: null argument");
+  IQSB_REQUIRE(nbits < 31 && (1 << nbits) == nranks && rank >= 0 && rank < nranks, "iqsb_plan_permute_global_bits: %u rank bits do not describe rank %d of %d",
+               nbits, rank, nranks);
   unsigned inverse[32], seen = 0;
   for (unsigned b = 0; b < nbits; ++b) {
-    IQSB_REQUIRE(dst_rank_bit[b] < nbits && !((seen >> dst_rank_bit[b]) & 1u), "iqsb_permute_global_bits: not a permutation of the rank bits");
+    IQSB_REQUIRE(dst_rank_bit[b] < nbits && !((seen >> dst_rank_bit[b]) & 1u), "iqsb_plan_permute_global_bits: not a permutation of the rank bits");
     seen |= 1u << dst_rank_bit[b];
     inverse[dst_rank_bit[b]] = b;
   }
-  bool involution = true, identity = true;
-  int destination = 0, source = 0;
+  bool involution = true, same = true;
+  int dst = 0, src = 0;
   for (unsigned b = 0; b < nbits; ++b) {
     involution = involution && dst_rank_bit[dst_rank_bit[b]] == b;
-    identity = identity && dst_rank_bit[b] == b;
-    if ((ctx->rank >> b) & 1) {
-      destination |= 1 << dst_rank_bit[b];  // my bit b travels to bit dst[b]
-      source |= 1 << inverse[b];            // my bit b is filled from bit inverse[b] of the source rank
-    }
+    same = same && dst_rank_bit[b] == b;
+    if ((rank >> b) & 1) dst |= 1 << dst_rank_bit[b];        // my bit b travels to bit dst[b]
+    if ((rank >> dst_rank_bit[b]) & 1) src |= 1 << b;        // my bit dst[b] is filled from bit b of the source rank
   }
+  (void)inverse;
+  *source = src;
+  *destination = dst;
+  *pairwise = involution ? 1 : 0;
+  *identity = same ? 1 : 0;
+  return IQSB_OK;
+}
+
+extern "C" int iqsb_permute_global_bits(iqsb_state *st, const uint8_t *dst_rank_bit, unsigned nbits) {
+  IQSB_REQUIRE(st && dst_rank_bit, "iqsb_permute_global_bits: null argument");
+  iqsb_ctx *ctx = st->ctx;
+  int source = 0, destination = 0, pairwise = 0, identity = 0;
+  IQSB_TRY(iqsb_plan_permute_global_bits(ctx->rank, ctx->nranks, dst_rank_bit, nbits, &source, &destination, &pairwise, &identity));
   if (identity) return IQSB_OK;
-  return permute_global_impl(st, source, destination, involution ? 1 : 0);
+  return permute_global_impl(st, source, destination, pairwise);
 }

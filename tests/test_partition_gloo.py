@@ -161,3 +161,68 @@ def test_plan_properties_single_process():
                 assert all(((r >> 0) & 1) == ((r >> 1) & 1) for r in idle)
     with pytest.raises(capi.IqsbError):
         capi.plan_global(0, 0, 2, 5, 0, 3)  # not a global position
+
+
+# ---- whole-shard moves when the rank bits are permuted (iqsb_permute_global_bits) ----------------
+def permute_worker(rank, world, port, M, perms, out_q):
+    sys.path.insert(0, HERE)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L = 1 << M
+    k = int(np.log2(world))
+    ok, msg = True, ""
+    for dst_bits in perms:
+        # shard of rank r: the global indices it holds (canonical placement)
+        shard = np.arange(rank * L, (rank + 1) * L, dtype=np.int64)
+        src, dst, pairwise, identity = capi.plan_permute_global_bits(rank, world, dst_bits)
+        plans = [None] * world
+        dist.all_gather_object(plans, (src, dst, pairwise, identity))
+        # every rank reached the same decision about the path without talking to anybody
+        if len({p[2] for p in plans}) != 1 or len({p[3] for p in plans}) != 1:
+            ok, msg = False, f"{dst_bits}: ranks disagree on the path"
+        if plans[src][1] != rank or plans[dst][0] != rank:
+            ok, msg = False, f"{dst_bits}: source / destination are not inverse of each other"
+        if pairwise != all(p[0] == p[1] for p in plans):
+            ok, msg = False, f"{dst_bits}: 'pairwise' does not mean every rank trades with one partner"
+        gathered = [torch.zeros(L, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(shard))
+        new_shard = gathered[src].numpy()  # "peer memory": pull the source's shard
+        # oracle: old global index i lands on j = i with its rank bits permuted
+        old = np.arange(world * L, dtype=np.int64)
+        r_old = old >> M
+        r_new = np.zeros_like(r_old)
+        for b in range(k):
+            r_new |= ((r_old >> b) & 1) << dst_bits[b]
+        j = (r_new << M) | (old & (L - 1))
+        want = np.empty_like(old)
+        want[j] = old
+        if not np.array_equal(new_shard, want[rank * L : (rank + 1) * L]):
+            ok, msg = False, f"{dst_bits}: rank {rank} holds the wrong shard"
+        if identity != (list(dst_bits) == list(range(k))):
+            ok, msg = False, f"{dst_bits}: identity flag"
+        if not ok:
+            break
+    flags = [None] * world
+    dist.all_gather_object(flags, (ok, msg))
+    if rank == 0:
+        out_q.put(flags)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_rank_bit_permutation_plan(world):
+    import itertools
+
+    k = int(np.log2(world))
+    perms = [list(p) for p in itertools.permutations(range(k))]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=permute_worker, args=(r, world, port, 3, perms, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    flags = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+    for ok, msg in flags:
+        assert ok, msg

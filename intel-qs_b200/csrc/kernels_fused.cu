@@ -103,6 +103,24 @@ struct BatchHdr {
   int ngroups, ngates, pad0, pad1;
 };
 
+#ifndef IQSB_FUSED_PARAMS
+#define IQSB_FUSED_PARAMS 1  // 1: the descriptors of a launch travel as a __grid_constant__ kernel parameter
+#endif
+// Descriptors of one launch in the kernel's parameter space (constant bank): group headers and gates are
+// read with warp-uniform indices through the constant cache -- they cost no shared-memory wavefronts, which
+// is what the tile phase is short of -- and only the per-lane slot tables go to shared memory.
+struct GroupHdr {
+  uint16_t p[4];
+  uint16_t gate_first, gate_count, log2_threads, pad;
+};
+template <typename T>
+struct RunParams {
+  int ngroups, pad0, pad1, pad2;
+  GroupHdr hdr[kBatchGroups];
+  uint16_t lohi[kBatchGroups][48];  // lo[32] then hi[16] of every group
+  FGate<T> gates[kBatchGates];
+};
+
 template <typename T>
 __host__ __device__ constexpr size_t batch_stride() {
   return sizeof(BatchHdr) + kBatchGroups * sizeof(GroupDesc) + kBatchGates * sizeof(FGate<T>);
@@ -424,6 +442,107 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
   }
 }
 
+template <typename T, bool FMA>
+__global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
+    k_fused_p(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, unsigned long long *__restrict__ next_tile, int debug_no_io,
+              const __grid_constant__ RunParams<T> P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cx<T> *tile = reinterpret_cast<Cx<T> *>(smem_raw);
+  __shared__ uint32_t g_lo[256], g_hi[8];
+  __shared__ uint16_t s_lohi[kBatchGroups][48];
+  __shared__ int s_pos[16];
+  __shared__ unsigned long long s_tile;
+  const int nS = td.nS;  // pos[0] == 0 always
+  if (threadIdx.x < kTile) s_pos[threadIdx.x] = td.pos[threadIdx.x];
+  for (int i = threadIdx.x; i < P.ngroups * 48; i += kThreads) s_lohi[i / 48][i % 48] = P.lohi[i / 48][i % 48];
+  __syncthreads();
+  for (unsigned t = threadIdx.x; t < 256 + 8; t += kThreads) {
+    unsigned v = t < 256 ? t : (t - 256) << 8;
+    uint32_t go = 0;
+#pragma unroll 1
+    for (int k = 1; k < nS; ++k)
+      if ((v >> (k - 1)) & 1u) go |= 1u << (s_pos[k] - 1);
+    if (t < 256) g_lo[t] = go;
+    else g_hi[t - 256] = go;
+  }
+  __syncthreads();
+  const unsigned nchunks = 1u << (nS - 1);
+  const int ngroups = P.ngroups;
+  for (unsigned it = 0;; ++it) {
+    if (threadIdx.x == 0) {
+      uint64_t o = next_tile != nullptr ? atomicAdd(next_tile, 1ull) : (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
+      uint64_t base = ~0ull;
+      if (o < nouter) {
+        base = o;
+#pragma unroll 1
+        for (int k = 0; k < nS; ++k) base = insert_zero(base, (unsigned)s_pos[k]);
+      }
+      s_tile = base;
+    }
+    __syncthreads();
+    if (s_tile == ~0ull) break;
+    if (!debug_no_io) {
+      tile_load_async<T>(tile, state + (s_tile >> 1), g_lo, g_hi, nchunks);
+      cp_async_wait<0>();
+    }
+    __syncthreads();  // the tile is loaded
+#pragma unroll 1
+    for (int gi = 0; gi < ngroups; ++gi) {
+      const GroupHdr &H = P.hdr[gi];
+      auto slots = [&](unsigned px, unsigned (&sl)[kAmps]) {
+        unsigned Pq[kRegBits];
+#pragma unroll
+        for (int j = 0; j < kRegBits; ++j) Pq[j] = H.p[j];
+#pragma unroll
+        for (int r = 0; r < kAmps; ++r) {
+          unsigned sidx = px;
+#pragma unroll
+          for (int j = 0; j < kRegBits; ++j)
+            if (r & (1 << j)) sidx ^= Pq[j];
+          sl[r] = sidx;
+        }
+      };
+      const unsigned nthr = 1u << H.log2_threads;
+#pragma unroll 1
+      for (unsigned t = threadIdx.x; t < nthr; t += kThreads) {
+        Cx<T> a[kAmps];
+        const unsigned px = (unsigned)s_lohi[gi][t & 31u] ^ (unsigned)s_lohi[gi][32 + (t >> 5)];
+        {
+          unsigned sl[kAmps];
+          slots(px, sl);
+#pragma unroll
+          for (int r = 0; r < kAmps; ++r) a[r] = tile[sl[r]];
+        }
+        bool more = true;
+#pragma unroll 1
+        for (int gj = H.gate_first; more; ++gj) {
+          const FGate<T> &fg = P.gates[gj];
+          const unsigned cls = fg.cls, tbit = fg.tbit, ckind = fg.ckind, c = fg.c, en = fg.en;
+          more = fg.last == 0;
+          if (ckind == 3 && !((s_tile >> c) & 1ull)) continue;  // uniform over the CTA
+          if (ckind == 2 && !((t >> c) & 1u)) continue;       // uniform over the warp when c >= 5 (the planner's choice)
+          if (tbit == 0) apply_on_bit<T, FMA, 0>(cls, en, fg.m, a);
+          else if (tbit == 1) apply_on_bit<T, FMA, 1>(cls, en, fg.m, a);
+          else if (kRegBits == 3 || tbit == 2) apply_on_bit<T, FMA, 2>(cls, en, fg.m, a);
+          else apply_on_bit<T, FMA, kRegBits - 1>(cls, en, fg.m, a);
+        }
+        {
+          unsigned sl[kAmps];
+          slots(px, sl);
+#pragma unroll
+          for (int r = 0; r < kAmps; ++r) tile[sl[r]] = a[r];
+        }
+      }
+      __syncthreads();
+    }
+    Chunk<T> *g = state + (s_tile >> 1);
+    if (debug_no_io) {
+    } else if (nchunks % (kThreads * 2) == 0) tile_store<T, 2>(tile, g, g_lo, g_hi, nchunks);
+    else tile_store<T, 1>(tile, g, g_lo, g_hi, nchunks);
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: classification, groups, descriptors
 // ---------------------------------------------------------------------------------------------
@@ -627,6 +746,50 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run
   int nbatches = 0;
   build_batches<T>(in, run, td, reorder, blob, nbatches);
   if (nbatches == 0) return IQSB_OK;
+  size_t smem = (size_t)sizeof(Cx<T>) << td.nS;
+#if IQSB_FUSED_PARAMS
+  {
+    // one launch (one sweep) per batch of descriptors: a run of more than kBatchGates gates on one tile
+    // pays an extra sweep per 48 gates
+    auto kernel_p = ctx->arith == IQSB_ARITH_FMA ? k_fused_p<T, true> : k_fused_p<T, false>;
+    IQSB_CUDA(cudaFuncSetAttribute(kernel_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm_p = 1;
+    IQSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, kernel_p, kThreads, smem));
+    if (per_sm_p < 1) per_sm_p = 1;
+    const uint64_t nouter_p = st->local_amps >> td.nS;
+    const uint64_t cap_p = (uint64_t)ctx->num_sms * per_sm_p;
+    const unsigned grid_p = (unsigned)(nouter_p < cap_p ? nouter_p : cap_p);
+    const char *dbg_p = getenv("IQS_B200_FUSED_DEBUG");
+    const int no_io_p = dbg_p && strcmp(dbg_p, "noio") == 0;
+    static RunParams<T> params;  // (host copy; the launch copies it into the parameter bank)
+    for (int b = 0; b < nbatches; ++b) {
+      const unsigned char *base = blob.data() + (size_t)b * batch_stride<T>();
+      const BatchHdr *h = reinterpret_cast<const BatchHdr *>(base);
+      const GroupDesc *gd = reinterpret_cast<const GroupDesc *>(base + sizeof(BatchHdr));
+      const FGate<T> *fg = reinterpret_cast<const FGate<T> *>(base + sizeof(BatchHdr) + kBatchGroups * sizeof(GroupDesc));
+      memset(&params, 0, sizeof(params));
+      params.ngroups = h->ngroups;
+      for (int gi = 0; gi < h->ngroups; ++gi) {
+        memcpy(params.hdr[gi].p, gd[gi].p, sizeof(gd[gi].p));
+        params.hdr[gi].gate_first = gd[gi].gate_first;
+        params.hdr[gi].gate_count = gd[gi].gate_count;
+        params.hdr[gi].log2_threads = gd[gi].log2_threads;
+        memcpy(&params.lohi[gi][0], gd[gi].lo, sizeof(gd[gi].lo));
+        memcpy(&params.lohi[gi][32], gd[gi].hi, sizeof(gd[gi].hi));
+      }
+      memcpy(params.gates, fg, (size_t)h->ngates * sizeof(FGate<T>));
+      unsigned long long *counter_p = nullptr;
+      if (dynamic_tiles()) {
+        if (!ctx->d_tile_counter) IQSB_CUDA(cudaMalloc((void **)&ctx->d_tile_counter, sizeof(unsigned long long)));
+        counter_p = ctx->d_tile_counter;
+        IQSB_CUDA(cudaMemsetAsync(counter_p, 0, sizeof(unsigned long long), ctx->stream));
+      }
+      kernel_p<<<grid_p, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter_p, td, counter_p, no_io_p, params);
+      IQSB_TRY(iqsb_check_launch(ctx, "k_fused", 2.0 * (double)st->local_amps * st->amp_bytes()));
+    }
+    return IQSB_OK;
+  }
+#endif
   // descriptors travel through the context's staging ring: written into pinned memory, copied in
   // stream order; the host only waits when the ring wraps around
   const size_t bytes = blob.size();
@@ -644,7 +807,6 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run
   unsigned char *d = ctx->stage_d + ctx->stage_off;
   IQSB_CUDA(cudaMemcpyAsync(d, ctx->stage_h + ctx->stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stage_off += (bytes + 255) & ~(size_t)255;
-  size_t smem = (size_t)sizeof(Cx<T>) << td.nS;
   auto kernel = ctx->arith == IQSB_ARITH_FMA ? k_fused<T, true> : k_fused<T, false>;
   IQSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;

@@ -5,10 +5,8 @@ set -e
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()" >/dev/null
 variants=(
-  "t12th256mb3:"
-  "t11th128mb6:-DIQSB_FUSED_TILE=11 -DIQSB_FUSED_THREADS=128 -DIQSB_FUSED_MINBLOCKS=6"
-  "t11th256mb3:-DIQSB_FUSED_TILE=11"
-  "t12th128mb3:-DIQSB_FUSED_THREADS=128 -DIQSB_FUSED_MINBLOCKS=3"
+  "params:"
+  "smemdesc:-DIQSB_FUSED_PARAMS=0"
 )
 for v in "${variants[@]}"; do
   name=${v%%:*}; flags=${v#*:}

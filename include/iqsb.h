@@ -187,12 +187,17 @@ int iqsb_plan_fused_order(const iqsb_fgate *gates, int ngates, unsigned log2_loc
  * descriptors the kernel reads.  out[k] = the k-th gate executed: its index in gates[], its run, its
  * group (numbered over all runs), its arithmetic class (0 general, 1 real, 2 diagonal, 3 diag(1,d),
  * 4 anti-diagonal, 5 exact X, 6 real diagonal + imaginary off-diagonal, 7 sqrt X, 8 sqrt Y), the
- * register bit of its target and the kind of its control (0 none, 1 register bit, 2 thread bit,
- * 3 bit of the tile's base index).  group_pos[4 g + j] = position held by register bit j of group g
+ * register bit of its target, the kind of its control (0 none, 1 register bit, 2 thread bit,
+ * 3 bit of the tile's base index) and whether it is applied to the registers or folded into the
+ * write-back addresses of its group.  group_pos[4 g + j] = position held by register bit j of group g
  * (255 = unused); group_pos holds 4 bytes per gate at most. */
 typedef struct iqsb_fused_trace {
   int32_t gate, run, group;
   uint8_t cls, tbit, ckind, c;
+  uint8_t trail; /* 0: applied to the registers; 1 / 2: exact X / CNOT at the end of its group, folded into the
+                  * write-back addresses (1: conditional offset, 2: absorbed into the basis) -- such gates take
+                  * effect in program order whatever their place in this list */
+  uint8_t pad[3];
 } iqsb_fused_trace;
 int iqsb_plan_fused_trace(const iqsb_fgate *gates, int ngates, unsigned log2_local, int reorder, iqsb_fused_trace *out, uint8_t *group_pos,
                           int *ngroups);

@@ -122,7 +122,8 @@ def plan_fused_order(gates, log2_local, reorder=True):
 
 class FusedTrace(ctypes.Structure):
     _fields_ = [("gate", ctypes.c_int32), ("run", ctypes.c_int32), ("group", ctypes.c_int32),
-                ("cls", ctypes.c_uint8), ("tbit", ctypes.c_uint8), ("ckind", ctypes.c_uint8), ("c", ctypes.c_uint8)]
+                ("cls", ctypes.c_uint8), ("tbit", ctypes.c_uint8), ("ckind", ctypes.c_uint8), ("c", ctypes.c_uint8),
+                ("trail", ctypes.c_uint8), ("pad", ctypes.c_uint8 * 3)]
 
 
 def plan_fused_trace(gates, log2_local, reorder=True):
@@ -133,7 +134,7 @@ def plan_fused_trace(gates, log2_local, reorder=True):
     gpos = np.zeros(4 * max(n, 1), dtype=np.uint8)
     ng = c_int()
     _chk(load().iqsb_plan_fused_trace(arr, n, log2_local, int(bool(reorder)), out, gpos.ctypes.data_as(c_vp), ctypes.byref(ng)))
-    trace = [dict(gate=out[k].gate, run=out[k].run, group=out[k].group, cls=out[k].cls, tbit=out[k].tbit, ckind=out[k].ckind, c=out[k].c) for k in range(n)]
+    trace = [dict(gate=out[k].gate, run=out[k].run, group=out[k].group, cls=out[k].cls, tbit=out[k].tbit, ckind=out[k].ckind, c=out[k].c, trail=out[k].trail) for k in range(n)]
     groups = [[int(p) for p in gpos[4 * g : 4 * g + 4] if p != 255] for g in range(ng.value)]
     return trace, groups
 

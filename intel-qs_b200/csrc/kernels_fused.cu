@@ -83,36 +83,41 @@ struct alignas(16) FGate {
   uint8_t ckind;  // 0 none | 1 register bit (pairs enabled: `en`) | 2 thread bit `c` | 3 bit `c` of the tile's base index
   uint8_t c;
   uint8_t en;     // mask of the kAmps/2 register pairs the gate acts on
-  uint8_t last;   // 1: last gate of its group
-  uint8_t pad8[2];
+  uint8_t last;   // 1: last gate of the group's main section
+  uint8_t trail;  // 0: applied to the registers | 1: exact X whose control is a thread / tile bit, folded into the
+                  //    write-back address (`pu`) | 2: exact X / CNOT absorbed into the group's write-back basis
+  uint8_t pad8;
   uint32_t origin;  // index of the gate in the caller's list (iqsb_plan_fused_trace)
-  uint32_t pad32;
+  uint16_t pu;      // trail == 1: swizzled slot offset XORed into the write-back address when the control is set
+  uint16_t pad16;
 };
 
 struct alignas(16) GroupDesc {
   uint16_t lo[32];  // swizzled slot contributed by thread bits 0..4
   uint16_t hi[16];  // ... by thread bits 5..8
-  uint16_t p[4];    // swizzled slot offset of register bit k
-  uint16_t gate_first, gate_count;
+  uint16_t p[4];    // swizzled slot offset of register bit k (where the registers are loaded from)
+  uint16_t gate_first, gate_count;  // all gates of the group: main section, then trail == 1, then trail == 2
   uint16_t log2_threads;  // tile exponent - kRegBits
-  uint16_t pad;
+  uint16_t nmain, ncond;  // gates applied to the registers / conditional write-back offsets
+  uint16_t w[4];          // write-back basis: register r goes to slot px ^ c0 ^ XOR_j r_j w[j]
+  uint16_t c0;
+  uint16_t pad[2];
 };
-static_assert(sizeof(GroupDesc) == 112, "group descriptor layout");
+static_assert(sizeof(GroupDesc) == 128, "group descriptor layout");
 
 struct BatchHdr {
   int ngroups, ngates, pad0, pad1;
 };
 
-#ifndef IQSB_FUSED_PARAMS
-#define IQSB_FUSED_PARAMS 1  // 1: the descriptors of a launch travel as a __grid_constant__ kernel parameter
-#endif
 // Descriptors of one launch in the kernel's parameter space (constant bank): group headers and gates are
 // read with warp-uniform indices through the constant cache -- they cost no shared-memory wavefronts, which
 // is what the tile phase is short of -- and only the per-lane slot tables go to shared memory.
 struct GroupHdr {
   uint16_t p[4];
-  uint16_t gate_first, gate_count, log2_threads, pad;
+  uint16_t w[4];
+  uint16_t gate_first, nmain, ncond, log2_threads, c0, pad[3];
 };
+static_assert(sizeof(GroupHdr) == 32, "group header layout");
 template <typename T>
 struct RunParams {
   int ngroups, pad0, pad1, pad2;
@@ -315,136 +320,7 @@ __device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Ma
 
 template <typename T, bool FMA>
 __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
-    k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, const unsigned char *__restrict__ desc, int nbatches,
-            unsigned long long *__restrict__ next_tile, int debug_no_io) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Cx<T> *tile = reinterpret_cast<Cx<T> *>(smem_raw);
-  // chunk offset of tile-local chunk index c = lo | hi << 8 (c = tile-local amplitude index / 2)
-  __shared__ uint32_t g_lo[256], g_hi[8];
-  __shared__ __align__(16) GroupDesc s_group[kBatchGroups];
-  __shared__ __align__(16) FGate<T> s_gate[kBatchGates];
-  __shared__ int s_pos[16];
-  __shared__ int s_hdr[4];
-  __shared__ unsigned long long s_tile;
-  const int nS = td.nS;  // pos[0] == 0 always
-  if (threadIdx.x < kTile) s_pos[threadIdx.x] = td.pos[threadIdx.x];
-  __syncthreads();
-  for (unsigned t = threadIdx.x; t < 256 + 8; t += kThreads) {
-    unsigned v = t < 256 ? t : (t - 256) << 8;
-    uint32_t go = 0;
-#pragma unroll 1
-    for (int k = 1; k < nS; ++k)
-      if ((v >> (k - 1)) & 1u) go |= 1u << (s_pos[k] - 1);
-    if (t < 256) g_lo[t] = go;
-    else g_hi[t - 256] = go;
-  }
-  auto stage = [&](int b) {
-    const unsigned char *src = desc + (size_t)b * batch_stride<T>();
-    const BatchHdr h = *reinterpret_cast<const BatchHdr *>(src);
-    if (threadIdx.x == 0) {
-      s_hdr[0] = h.ngroups;
-      s_hdr[1] = h.ngates;
-    }
-    const int4 *gs = reinterpret_cast<const int4 *>(src + sizeof(BatchHdr));
-    const int ng4 = h.ngroups * (int)(sizeof(GroupDesc) / 16);
-    for (int i = threadIdx.x; i < ng4; i += kThreads) reinterpret_cast<int4 *>(s_group)[i] = __ldg(gs + i);
-    const int4 *fs = reinterpret_cast<const int4 *>(src + sizeof(BatchHdr) + kBatchGroups * sizeof(GroupDesc));
-    const int nf4 = h.ngates * (int)(sizeof(FGate<T>) / 16);
-    for (int i = threadIdx.x; i < nf4; i += kThreads) reinterpret_cast<int4 *>(s_gate)[i] = __ldg(fs + i);
-  };
-  if (nbatches == 1) stage(0);
-  __syncthreads();
-  const unsigned nchunks = 1u << (nS - 1);
-  // Tiles are handed out in address order from a global counter (next_tile != nullptr): the CTAs of
-  // the whole GPU then work inside one moving window of the state, whatever their individual pace.
-  // Thread 0 publishes the tile's base index (amplitude index with zeros at the tile positions) in
-  // shared memory; nothing 64-bit has to stay in registers across the arithmetic.
-  for (unsigned it = 0;; ++it) {
-    if (threadIdx.x == 0) {
-      uint64_t o = next_tile != nullptr ? atomicAdd(next_tile, 1ull) : (uint64_t)blockIdx.x + (uint64_t)it * gridDim.x;
-      uint64_t base = ~0ull;
-      if (o < nouter) {
-        base = o;
-#pragma unroll 1
-        for (int k = 0; k < nS; ++k) base = insert_zero(base, (unsigned)s_pos[k]);
-      }
-      s_tile = base;
-    }
-    __syncthreads();
-    if (s_tile == ~0ull) break;
-    if (!debug_no_io) {  // (IQS_B200_FUSED_DEBUG=noio times the tile phase alone: the state is not touched)
-      tile_load_async<T>(tile, state + (s_tile >> 1), g_lo, g_hi, nchunks);
-      cp_async_wait<0>();
-    }
-    for (int b = 0; b < nbatches; ++b) {
-      if (nbatches > 1) {
-        if (b) __syncthreads();  // nobody still reads the previous batch
-        stage(b);
-      }
-      __syncthreads();  // the tile is loaded, the descriptors are visible
-      const int ngroups = s_hdr[0];
-      for (int gi = 0; gi < ngroups; ++gi) {
-        // The group's addressing (a few 16-bit table entries) is read again for the write-back instead
-        // of being kept in registers across the gates -- the volatile reads stop the compiler from
-        // carrying (and spilling) ~17 registers of addresses through the arithmetic.
-        const volatile GroupDesc *G = &s_group[gi];
-        auto slots = [&](unsigned t, unsigned (&sl)[kAmps]) {
-          const unsigned px = (unsigned)G->lo[t & 31u] ^ (unsigned)G->hi[t >> 5];
-          unsigned P[kRegBits];
-#pragma unroll
-          for (int j = 0; j < kRegBits; ++j) P[j] = G->p[j];
-#pragma unroll
-          for (int r = 0; r < kAmps; ++r) {
-            unsigned sidx = px;
-#pragma unroll
-            for (int j = 0; j < kRegBits; ++j)
-              if (r & (1 << j)) sidx ^= P[j];
-            sl[r] = sidx;
-          }
-        };
-#pragma unroll 1
-        for (unsigned t = threadIdx.x; t < (1u << G->log2_threads); t += kThreads) {
-          Cx<T> a[kAmps];
-          {
-            unsigned sl[kAmps];
-            slots(t, sl);
-#pragma unroll
-            for (int r = 0; r < kAmps; ++r) a[r] = tile[sl[r]];
-          }
-          bool more = true;
-#pragma unroll 1
-          for (int gj = G->gate_first; more; ++gj) {
-            const FGate<T> &fg = s_gate[gj];
-            const unsigned cls = fg.cls, tbit = fg.tbit, ckind = fg.ckind, c = fg.c, en = fg.en;
-            more = fg.last == 0;
-            if (ckind == 3 && !((s_tile >> c) & 1ull)) continue;  // uniform over the CTA
-            if (ckind == 2 && !((t >> c) & 1u)) continue;       // uniform over the warp when c >= 5 (the planner's choice)
-            if (tbit == 0) apply_on_bit<T, FMA, 0>(cls, en, fg.m, a);
-            else if (tbit == 1) apply_on_bit<T, FMA, 1>(cls, en, fg.m, a);
-            else if (kRegBits == 3 || tbit == 2) apply_on_bit<T, FMA, 2>(cls, en, fg.m, a);
-            else apply_on_bit<T, FMA, kRegBits - 1>(cls, en, fg.m, a);
-          }
-          {
-            unsigned sl[kAmps];
-            slots(t, sl);
-#pragma unroll
-            for (int r = 0; r < kAmps; ++r) tile[sl[r]] = a[r];
-          }
-        }
-        __syncthreads();
-      }
-    }
-    Chunk<T> *g = state + (s_tile >> 1);
-    if (debug_no_io) {
-    } else if (nchunks % (kThreads * 2) == 0) tile_store<T, 2>(tile, g, g_lo, g_hi, nchunks);
-    else tile_store<T, 1>(tile, g, g_lo, g_hi, nchunks);
-    __syncthreads();
-  }
-}
-
-template <typename T, bool FMA>
-__global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
-    k_fused_p(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, unsigned long long *__restrict__ next_tile, int debug_no_io,
+    k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, unsigned long long *__restrict__ next_tile, int debug_no_io,
               const __grid_constant__ RunParams<T> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cx<T> *tile = reinterpret_cast<Cx<T> *>(smem_raw);
@@ -489,10 +365,10 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
 #pragma unroll 1
     for (int gi = 0; gi < ngroups; ++gi) {
       const GroupHdr &H = P.hdr[gi];
-      auto slots = [&](unsigned px, unsigned (&sl)[kAmps]) {
+      auto slots = [&](unsigned px, const uint16_t (&basis)[4], unsigned (&sl)[kAmps]) {
         unsigned Pq[kRegBits];
 #pragma unroll
-        for (int j = 0; j < kRegBits; ++j) Pq[j] = H.p[j];
+        for (int j = 0; j < kRegBits; ++j) Pq[j] = basis[j];
 #pragma unroll
         for (int r = 0; r < kAmps; ++r) {
           unsigned sidx = px;
@@ -509,11 +385,11 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
         const unsigned px = (unsigned)s_lohi[gi][t & 31u] ^ (unsigned)s_lohi[gi][32 + (t >> 5)];
         {
           unsigned sl[kAmps];
-          slots(px, sl);
+          slots(px, H.p, sl);
 #pragma unroll
           for (int r = 0; r < kAmps; ++r) a[r] = tile[sl[r]];
         }
-        bool more = true;
+        bool more = H.nmain != 0;
 #pragma unroll 1
         for (int gj = H.gate_first; more; ++gj) {
           const FGate<T> &fg = P.gates[gj];
@@ -527,8 +403,19 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
           else apply_on_bit<T, FMA, kRegBits - 1>(cls, en, fg.m, a);
         }
         {
+          // Exact X / CNOT gates at the end of a group never touch the registers: a permutation of the
+          // 8 amplitudes is a change of the basis (w, c0) the write-back addresses are built from, and an
+          // X whose control is a thread bit or a bit of the tile's base index is one more conditional offset.
+          unsigned pxs = px ^ H.c0;
+#pragma unroll 1
+          for (int gj = H.gate_first + H.nmain, ge = gj + H.ncond; gj < ge; ++gj) {
+            const FGate<T> &fg = P.gates[gj];
+            const unsigned c = fg.c;
+            const bool on = fg.ckind == 2 ? ((t >> c) & 1u) != 0u : ((s_tile >> c) & 1ull) != 0ull;
+            if (on) pxs ^= fg.pu;
+          }
           unsigned sl[kAmps];
-          slots(px, sl);
+          slots(pxs, H.w, sl);
 #pragma unroll
           for (int r = 0; r < kAmps; ++r) tile[sl[r]] = a[r];
         }
@@ -697,29 +584,79 @@ void build_batches(const iqsb_fgate *in, const std::vector<int> &run, const Tile
       gd.hi[v] = (uint16_t)swz(x);
     }
     for (int j = 0; j < kRegBits; ++j) gd.p[j] = (uint16_t)swz(1u << hg.rs[j]);
+    auto regbit = [&](int slot) {
+      for (int j = 0; j < kRegBits; ++j)
+        if (hg.rs[j] == slot) return j;
+      return -1;
+    };
+    // Which exact X / CNOT gates can be taken out of the arithmetic: walking backwards, a permutation gate
+    // that shares no qubit with any gate staying behind it commutes with those exactly, so it can run last
+    // -- and a permutation of the 8 register-resident amplitudes run last is only a different write-back
+    // address.  trail[k]: 0 main, 1 conditional offset (control on a thread / tile bit), 2 absorbed.
+    std::vector<uint8_t> trail(hg.gates.size(), 0);
+    {
+      uint64_t main_q = 0;
+      for (int k = (int)hg.gates.size() - 1; k >= 0; --k) {
+        const iqsb_fgate &q = in[run[hg.gates[k]]];
+        const uint64_t qm = (1ull << (unsigned)q.target) | (q.kind == 1 ? 1ull << (unsigned)q.control : 0ull);
+        if (reorder && is_xexact(q.m) && !(qm & main_q)) {
+          const int cs = q.kind == 1 ? slot_of[q.control] : -1;
+          trail[k] = (q.kind == 1 && !(cs >= 0 && regbit(cs) >= 0)) ? 1 : 2;
+        } else {
+          main_q |= qm;
+        }
+      }
+    }
+    // the trailing gates as one affine map of the 3-bit register index: T(q) = A q + v0 + sum_i ctrl_i u_i
+    unsigned A[kRegBits], v0 = 0;
+    for (int j = 0; j < kRegBits; ++j) A[j] = 1u << j;
+    std::vector<std::pair<int, unsigned>> cond;  // (index into hg.gates, u)
+    for (size_t k = 0; k < hg.gates.size(); ++k) {
+      if (!trail[k]) continue;
+      const iqsb_fgate &q = in[run[hg.gates[k]]];
+      const int bt = regbit(slot_of[q.target]);
+      if (trail[k] == 1) {
+        cond.push_back({(int)k, 1u << bt});
+      } else if (q.kind == 0) {
+        v0 ^= 1u << bt;
+      } else {  // CNOT between two register bits: M = I + e_b e_c^T applied to everything so far
+        const int bc = regbit(slot_of[q.control]);
+        for (int j = 0; j < kRegBits; ++j)
+          if ((A[j] >> bc) & 1u) A[j] ^= 1u << bt;
+        if ((v0 >> bc) & 1u) v0 ^= 1u << bt;
+        for (auto &cu : cond)
+          if ((cu.second >> bc) & 1u) cu.second ^= 1u << bt;
+      }
+    }
+    auto span = [&](unsigned bits) {  // XOR of the load offsets of the register bits in `bits`
+      unsigned o = 0;
+      for (int j = 0; j < kRegBits; ++j)
+        if ((bits >> j) & 1u) o ^= gd.p[j];
+      return o;
+    };
+    for (int j = 0; j < kRegBits; ++j) gd.w[j] = (uint16_t)span(A[j]);
+    gd.c0 = (uint16_t)span(v0);
     gd.gate_first = (uint16_t)bgates.size();
     gd.gate_count = (uint16_t)hg.gates.size();
     gd.log2_threads = (uint16_t)ndep;
-    bgroups.push_back(gd);
-    for (int k : hg.gates) {
-      const iqsb_fgate &q = in[run[k]];
+    auto emit = [&](size_t k, uint8_t tr, unsigned pu) {
+      const iqsb_fgate &q = in[run[hg.gates[k]]];
       FGate<T> o;
       memset(&o, 0, sizeof(o));
       o.m = make_mat<T>(q.m);
       o.cls = classify(q.m);
-      o.origin = (uint32_t)run[k];
+      o.origin = (uint32_t)run[hg.gates[k]];
+      o.trail = tr;
+      o.pu = (uint16_t)pu;
       const int ts = slot_of[q.target];
-      for (int j = 0; j < kRegBits; ++j)
-        if (hg.rs[j] == ts) o.tbit = (uint8_t)j;
+      o.tbit = (uint8_t)regbit(ts);
       o.en = (uint8_t)((1u << (kAmps / 2)) - 1u);
       if (q.kind == 1) {
         const int cs = slot_of[q.control];
         if (cs < 0) { o.ckind = 3; o.c = (uint8_t)q.control; }
         else if (tbit_of[cs] >= 0) { o.ckind = 2; o.c = (uint8_t)tbit_of[cs]; }
         else {
-          int cb = 0;
-          for (int j = 0; j < kRegBits; ++j)
-            if (hg.rs[j] == cs) cb = j;
+          const int cb = regbit(cs);
           o.ckind = 1;
           o.c = (uint8_t)cb;
           o.en = 0;
@@ -730,15 +667,25 @@ void build_batches(const iqsb_fgate *in, const std::vector<int> &run, const Tile
         }
       }
       bgates.push_back(o);
-    }
-    bgates.back().last = 1;
+    };
+    int nmain = 0;
+    for (size_t k = 0; k < hg.gates.size(); ++k)
+      if (!trail[k]) { emit(k, 0, 0); ++nmain; }
+    if (nmain) bgates.back().last = 1;
+    for (auto &cu : cond) emit((size_t)cu.first, 1, span(cu.second));
+    for (size_t k = 0; k < hg.gates.size(); ++k)
+      if (trail[k] == 2) emit(k, 2, 0);
+    gd.nmain = (uint16_t)nmain;
+    gd.ncond = (uint16_t)cond.size();
+    bgroups.push_back(gd);
   }
   flush();
 }
 
 bool dynamic_tiles();
 
-// one run: the gates `run` (indices into `in`, execution order) all have their target in the tile `td`
+// one run: the gates `run` (indices into `in`, execution order) all have their target in the tile `td`.
+// One launch (one sweep) per batch of descriptors; the descriptors travel as a kernel parameter.
 template <typename T>
 int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run, const TileDesc &td, bool reorder) {
   iqsb_ctx *ctx = st->ctx;
@@ -746,85 +693,48 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run
   int nbatches = 0;
   build_batches<T>(in, run, td, reorder, blob, nbatches);
   if (nbatches == 0) return IQSB_OK;
-  size_t smem = (size_t)sizeof(Cx<T>) << td.nS;
-#if IQSB_FUSED_PARAMS
-  {
-    // one launch (one sweep) per batch of descriptors: a run of more than kBatchGates gates on one tile
-    // pays an extra sweep per 48 gates
-    auto kernel_p = ctx->arith == IQSB_ARITH_FMA ? k_fused_p<T, true> : k_fused_p<T, false>;
-    IQSB_CUDA(cudaFuncSetAttribute(kernel_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm_p = 1;
-    IQSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p, kernel_p, kThreads, smem));
-    if (per_sm_p < 1) per_sm_p = 1;
-    const uint64_t nouter_p = st->local_amps >> td.nS;
-    const uint64_t cap_p = (uint64_t)ctx->num_sms * per_sm_p;
-    const unsigned grid_p = (unsigned)(nouter_p < cap_p ? nouter_p : cap_p);
-    const char *dbg_p = getenv("IQS_B200_FUSED_DEBUG");
-    const int no_io_p = dbg_p && strcmp(dbg_p, "noio") == 0;
-    static RunParams<T> params;  // (host copy; the launch copies it into the parameter bank)
-    for (int b = 0; b < nbatches; ++b) {
-      const unsigned char *base = blob.data() + (size_t)b * batch_stride<T>();
-      const BatchHdr *h = reinterpret_cast<const BatchHdr *>(base);
-      const GroupDesc *gd = reinterpret_cast<const GroupDesc *>(base + sizeof(BatchHdr));
-      const FGate<T> *fg = reinterpret_cast<const FGate<T> *>(base + sizeof(BatchHdr) + kBatchGroups * sizeof(GroupDesc));
-      memset(&params, 0, sizeof(params));
-      params.ngroups = h->ngroups;
-      for (int gi = 0; gi < h->ngroups; ++gi) {
-        memcpy(params.hdr[gi].p, gd[gi].p, sizeof(gd[gi].p));
-        params.hdr[gi].gate_first = gd[gi].gate_first;
-        params.hdr[gi].gate_count = gd[gi].gate_count;
-        params.hdr[gi].log2_threads = gd[gi].log2_threads;
-        memcpy(&params.lohi[gi][0], gd[gi].lo, sizeof(gd[gi].lo));
-        memcpy(&params.lohi[gi][32], gd[gi].hi, sizeof(gd[gi].hi));
-      }
-      memcpy(params.gates, fg, (size_t)h->ngates * sizeof(FGate<T>));
-      unsigned long long *counter_p = nullptr;
-      if (dynamic_tiles()) {
-        if (!ctx->d_tile_counter) IQSB_CUDA(cudaMalloc((void **)&ctx->d_tile_counter, sizeof(unsigned long long)));
-        counter_p = ctx->d_tile_counter;
-        IQSB_CUDA(cudaMemsetAsync(counter_p, 0, sizeof(unsigned long long), ctx->stream));
-      }
-      kernel_p<<<grid_p, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter_p, td, counter_p, no_io_p, params);
-      IQSB_TRY(iqsb_check_launch(ctx, "k_fused", 2.0 * (double)st->local_amps * st->amp_bytes()));
-    }
-    return IQSB_OK;
-  }
-#endif
-  // descriptors travel through the context's staging ring: written into pinned memory, copied in
-  // stream order; the host only waits when the ring wraps around
-  const size_t bytes = blob.size();
-  if (!ctx->stage_h) {
-    IQSB_CUDA(cudaMallocHost((void **)&ctx->stage_h, kStageBytes));
-    IQSB_CUDA(cudaMalloc((void **)&ctx->stage_d, kStageBytes));
-    ctx->stage_off = 0;
-  }
-  IQSB_REQUIRE(bytes <= kStageBytes, "iqsb_fused: gate list too long for the staging ring");
-  if (ctx->stage_off + bytes > kStageBytes) {
-    IQSB_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->stage_off = 0;
-  }
-  memcpy(ctx->stage_h + ctx->stage_off, blob.data(), bytes);
-  unsigned char *d = ctx->stage_d + ctx->stage_off;
-  IQSB_CUDA(cudaMemcpyAsync(d, ctx->stage_h + ctx->stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  ctx->stage_off += (bytes + 255) & ~(size_t)255;
+  const size_t smem = (size_t)sizeof(Cx<T>) << td.nS;
   auto kernel = ctx->arith == IQSB_ARITH_FMA ? k_fused<T, true> : k_fused<T, false>;
   IQSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   IQSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  uint64_t nouter = st->local_amps >> td.nS;
-  uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
-  unsigned grid = (unsigned)(nouter < cap ? nouter : cap);
-  unsigned long long *counter = nullptr;
-  if (dynamic_tiles()) {
-    if (!ctx->d_tile_counter) IQSB_CUDA(cudaMalloc((void **)&ctx->d_tile_counter, sizeof(unsigned long long)));
-    counter = ctx->d_tile_counter;
-    IQSB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
-  }
+  const uint64_t nouter = st->local_amps >> td.nS;
+  const uint64_t cap = (uint64_t)ctx->num_sms * per_sm;
+  const unsigned grid = (unsigned)(nouter < cap ? nouter : cap);
   const char *dbg = getenv("IQS_B200_FUSED_DEBUG");
   const int no_io = dbg && strcmp(dbg, "noio") == 0;
-  kernel<<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, d, nbatches, counter, no_io);
-  return iqsb_check_launch(ctx, "k_fused", 2.0 * (double)st->local_amps * st->amp_bytes());
+  static thread_local RunParams<T> params;  // host copy; the launch copies it into the parameter bank
+  for (int b = 0; b < nbatches; ++b) {
+    const unsigned char *base = blob.data() + (size_t)b * batch_stride<T>();
+    const BatchHdr *h = reinterpret_cast<const BatchHdr *>(base);
+    const GroupDesc *gd = reinterpret_cast<const GroupDesc *>(base + sizeof(BatchHdr));
+    const FGate<T> *fg = reinterpret_cast<const FGate<T> *>(base + sizeof(BatchHdr) + kBatchGroups * sizeof(GroupDesc));
+    memset(&params, 0, sizeof(params));
+    params.ngroups = h->ngroups;
+    for (int gi = 0; gi < h->ngroups; ++gi) {
+      GroupHdr &o = params.hdr[gi];
+      memcpy(o.p, gd[gi].p, sizeof(o.p));
+      memcpy(o.w, gd[gi].w, sizeof(o.w));
+      o.gate_first = gd[gi].gate_first;
+      o.nmain = gd[gi].nmain;
+      o.ncond = gd[gi].ncond;
+      o.log2_threads = gd[gi].log2_threads;
+      o.c0 = gd[gi].c0;
+      memcpy(&params.lohi[gi][0], gd[gi].lo, sizeof(gd[gi].lo));
+      memcpy(&params.lohi[gi][32], gd[gi].hi, sizeof(gd[gi].hi));
+    }
+    memcpy(params.gates, fg, (size_t)h->ngates * sizeof(FGate<T>));
+    unsigned long long *counter = nullptr;
+    if (dynamic_tiles()) {
+      if (!ctx->d_tile_counter) IQSB_CUDA(cudaMalloc((void **)&ctx->d_tile_counter, sizeof(unsigned long long)));
+      counter = ctx->d_tile_counter;
+      IQSB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    kernel<<<grid, kThreads, smem, ctx->stream>>>((Chunk<T> *)st->d, nouter, td, counter, no_io, params);
+    IQSB_TRY(iqsb_check_launch(ctx, "k_fused", 2.0 * (double)st->local_amps * st->amp_bytes()));
+  }
+  return IQSB_OK;
 }
 
 // The planner.  order = gate indices in execution order, run_end[r] = one past the last entry of
@@ -976,6 +886,8 @@ extern "C" int iqsb_plan_fused_trace(const iqsb_fgate *gates, int ngates, unsign
           out[k].tbit = fg[q].tbit;
           out[k].ckind = fg[q].ckind;
           out[k].c = fg[q].c;
+          out[k].trail = fg[q].trail;
+          out[k].pad[0] = out[k].pad[1] = out[k].pad[2] = 0;
         }
       }
     }

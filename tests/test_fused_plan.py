@@ -143,9 +143,17 @@ def check_trace(gates, M, reorder=True):
                 assert g[1] not in regs
         else:
             assert t["ckind"] == 0
+    info = {t["gate"]: t for t in trace}
+    for t in trace:
+        if t["trail"]:
+            assert t["cls"] == CLS["x"] and reorder  # only exact X / CNOT are folded into the write-back addresses
+            assert (t["trail"] == 1) == (t["ckind"] in (2, 3))
     for i in range(len(gates)):
         for j in range(i + 1, len(gates)):
             if when[j] < when[i]:
+                a, b = info[i], info[j]
+                if a["trail"] and b["trail"] and a["group"] == b["group"]:
+                    continue  # both folded into the same write-back: composed in program order by construction
                 assert not (_qubits(gates[i]) & _qubits(gates[j])), (i, j)
                 assert _is_perm(gates[i]) or _is_perm(gates[j]), (i, j)
     return trace, groups
@@ -175,6 +183,7 @@ def test_schedule_of_a_bench_layer_absorbs_the_cnots():
         first_run = [t for t in trace if t["run"] == 0]
         assert len({t["group"] for t in first_run}) == 4
         assert sum(1 for t in first_run if t["cls"] == CLS["x"]) >= 5
+        assert all(t["trail"] for t in first_run if t["cls"] == CLS["x"])  # the CNOTs cost no instruction on the data
         assert len(groups) <= 12
 
 

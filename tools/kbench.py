@@ -129,6 +129,9 @@ def main():
         gates = [((1, int(op["q0"]), int(op["q1"])) if op["kind"] == C.CX else (0, 0, int(op["q0"]))) + (bench.named_matrix(C, int(op["kind"]), op["p"]),) for op in layer]
         runs = len(capi.plan_fused_order(gates, n))
         timeit(f"bench_layer0_{len(gates)}g{runs}r", "-", lambda gates=gates: st.fused(gates), 32.0 * L * runs)
+    if "fusedx" in ops:  # profiling target: 12 X gates on the 12 lowest positions = 4 groups, no arithmetic
+        gates = [(0, 0, i % 12, X) for i in range(12)]
+        timeit("fused12_x", "-", lambda gates=gates: st.fused(gates), 32.0 * L)
     if "gate2" in ops:
         rng = np.random.default_rng(0)
         q, _ = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))

@@ -24,7 +24,19 @@
 //          products with exact zeros and ones: 0-12 instead of 28 FP64 instructions per pair.  For
 //          finite amplitudes the values are identical to the reference's full evaluation (a product
 //          with an exact zero only contributes a signed zero); the reference does the same on the
-//          CPU for named gates (src/spec_kernels.cpp:36-153).
+//          CPU for named gates (src/spec_kernels.cpp:36-153).  sqrt X / sqrt Y (entries +-1/2 +- i/2) take
+//          12 instructions: halving is exact and commutes with the rounding of the sums.
+//   perm   an exact X / CNOT that shares no qubit with the gates after it in its group does not touch the
+//          registers at all: a permutation of the 8 register-resident amplitudes is an affine map of the
+//          3-bit register index over GF(2), composed on the host into the basis (w, c0) the write-back
+//          addresses are built from; an X whose control is a thread bit or a bit of the tile's base index
+//          is one conditional XOR on the address.  (As register moves these gates cost 5 ms per group and
+//          2^32 amplitudes; a group of them now runs at the shared-memory bandwidth, 4.3 ms.)
+//
+// Descriptors (group headers, gates with their matrices) travel as a __grid_constant__ kernel parameter:
+// they are read with warp-uniform indices through the constant cache and cost no shared-memory
+// wavefronts -- the resource the tile phase is short of; only the per-lane slot tables are staged in
+// shared memory.  One launch (one sweep) carries up to 24 groups / 48 gates.
 //
 // Planner (host, exposed as iqsb_plan_fused_order): runs are cut greedily in program order, but a
 // pure-permutation gate (X / CNOT with an exact 0/1 matrix) commutes EXACTLY -- no rounding is

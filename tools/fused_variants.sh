@@ -5,8 +5,8 @@ set -e
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()" >/dev/null
 variants=(
-  "params:"
-  "smemdesc:-DIQSB_FUSED_PARAMS=0"
+  "r3mb3:"
+  "r4mb2:-DIQSB_FUSED_REGBITS=4 -DIQSB_FUSED_MINBLOCKS=2"
 )
 for v in "${variants[@]}"; do
   name=${v%%:*}; flags=${v#*:}

@@ -57,19 +57,17 @@
 
 namespace {
 
-#ifndef IQSB_FUSED_MINBLOCKS
-#define IQSB_FUSED_MINBLOCKS 3
-#endif
+// Two CTA shapes, picked per batch of gates (iqsb_fused): tiles of 2^12 amplitudes worked on by 256 threads,
+// 3 CTAs per SM -- or tiles of 2^11 with 128 threads, 6 CTAs per SM, which interleave the phases of a run
+// more finely (5-6 % faster per run, sweeps at 105 % of the copy peak) but hold one target position less.
+// The smaller tile is used whenever it does not cost an extra run.
 #ifndef IQSB_FUSED_TILE
 #define IQSB_FUSED_TILE 12
 #endif
 #ifndef IQSB_FUSED_REGBITS
 #define IQSB_FUSED_REGBITS 3
 #endif
-#ifndef IQSB_FUSED_THREADS
-#define IQSB_FUSED_THREADS 256
-#endif
-constexpr int kThreads = IQSB_FUSED_THREADS;
+constexpr int kSmallTile = 11;
 constexpr int kMaxFusedGates = 4096;
 constexpr int kTile = IQSB_FUSED_TILE;  // tile exponent (<= 12)
 // (A variant with two tile buffers of 2^11 amplitudes per CTA, the next tile fetched while the current
@@ -162,7 +160,7 @@ __device__ __forceinline__ void cp_async_amp(Cx<float> *smem, const Cx<float> *g
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
 }
-template <typename T>
+template <typename T, int kThreads>
 __device__ __forceinline__ void tile_load_async(Cx<T> *tile, const Chunk<T> *g, const uint32_t *g_lo, const uint32_t *g_hi, unsigned nchunks) {
 #pragma unroll 4
   for (unsigned c = threadIdx.x; c < nchunks; c += kThreads) {
@@ -178,7 +176,7 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 // tile -> global, U 32-byte stores in flight per thread; nchunks is a multiple of kThreads * U
-template <typename T, int U>
+template <typename T, int U, int kThreads>
 __device__ __forceinline__ void tile_store(const Cx<T> *tile, Chunk<T> *g, const uint32_t *g_lo, const uint32_t *g_hi, unsigned nchunks) {
 #pragma unroll 1
   for (unsigned c0 = threadIdx.x; c0 < nchunks; c0 += kThreads * U) {
@@ -330,8 +328,8 @@ __device__ __forceinline__ void apply_on_bit(unsigned cls, unsigned en, const Ma
   }
 }
 
-template <typename T, bool FMA>
-__global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
+template <typename T, bool FMA, int kThreads>
+__global__ void __launch_bounds__(kThreads, 768 / kThreads)
     k_fused(Chunk<T> *__restrict__ state, uint64_t nouter, TileDesc td, unsigned long long *__restrict__ next_tile, int debug_no_io,
               const __grid_constant__ RunParams<T> P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -370,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
     __syncthreads();
     if (s_tile == ~0ull) break;
     if (!debug_no_io) {
-      tile_load_async<T>(tile, state + (s_tile >> 1), g_lo, g_hi, nchunks);
+      tile_load_async<T, kThreads>(tile, state + (s_tile >> 1), g_lo, g_hi, nchunks);
       cp_async_wait<0>();
     }
     __syncthreads();  // the tile is loaded
@@ -436,8 +434,8 @@ __global__ void __launch_bounds__(kThreads, IQSB_FUSED_MINBLOCKS)
     }
     Chunk<T> *g = state + (s_tile >> 1);
     if (debug_no_io) {
-    } else if (nchunks % (kThreads * 2) == 0) tile_store<T, 2>(tile, g, g_lo, g_hi, nchunks);
-    else tile_store<T, 1>(tile, g, g_lo, g_hi, nchunks);
+    } else if (nchunks % (kThreads * 2) == 0) tile_store<T, 2, kThreads>(tile, g, g_lo, g_hi, nchunks);
+    else tile_store<T, 1, kThreads>(tile, g, g_lo, g_hi, nchunks);
     __syncthreads();
   }
 }
@@ -698,15 +696,15 @@ bool dynamic_tiles();
 
 // one run: the gates `run` (indices into `in`, execution order) all have their target in the tile `td`.
 // One launch (one sweep) per batch of descriptors; the descriptors travel as a kernel parameter.
-template <typename T>
-int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run, const TileDesc &td, bool reorder) {
+template <typename T, int kThreads>
+int launch_run_shape(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run, const TileDesc &td, bool reorder) {
   iqsb_ctx *ctx = st->ctx;
   std::vector<unsigned char> blob;
   int nbatches = 0;
   build_batches<T>(in, run, td, reorder, blob, nbatches);
   if (nbatches == 0) return IQSB_OK;
   const size_t smem = (size_t)sizeof(Cx<T>) << td.nS;
-  auto kernel = ctx->arith == IQSB_ARITH_FMA ? k_fused<T, true> : k_fused<T, false>;
+  auto kernel = ctx->arith == IQSB_ARITH_FMA ? k_fused<T, true, kThreads> : k_fused<T, false, kThreads>;
   IQSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   IQSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
@@ -749,10 +747,17 @@ int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run
   return IQSB_OK;
 }
 
+// tiles of 2^12 amplitudes: 256 threads, 3 CTAs per SM; smaller tiles: 128 threads, 6 CTAs per SM
+template <typename T>
+int launch_run(iqsb_state *st, const iqsb_fgate *in, const std::vector<int> &run, const TileDesc &td, bool reorder) {
+  return td.nS > kSmallTile ? launch_run_shape<T, 256>(st, in, run, td, reorder) : launch_run_shape<T, 128>(st, in, run, td, reorder);
+}
+
 // The planner.  order = gate indices in execution order, run_end[r] = one past the last entry of
 // run r in `order`, tiles[r*16] = number of tile positions, tiles[r*16 + 1 ..] = the positions.
-int plan_runs(const iqsb_fgate *gates, int ngates, unsigned log2_local, bool reorder, int *order, int *run_end, uint8_t *tiles, int max_runs, int *nruns) {
-  const unsigned K = log2_local < (unsigned)kTile ? log2_local : (unsigned)kTile;
+int plan_runs_k(const iqsb_fgate *gates, int ngates, unsigned log2_local, bool reorder, unsigned tile_log2, int *order, int *run_end, uint8_t *tiles,
+                int max_runs, int *nruns) {
+  const unsigned K = log2_local < tile_log2 ? log2_local : tile_log2;
   const unsigned low = log2_local < (unsigned)kLow ? log2_local : (unsigned)kLow;
   std::vector<char> done((size_t)ngates, 0);
   int r = 0, first_pending = 0, nordered = 0;
@@ -806,6 +811,25 @@ int plan_runs(const iqsb_fgate *gates, int ngates, unsigned log2_local, bool reo
     run_end[r++] = nordered;
   }
   *nruns = r;
+  return IQSB_OK;
+}
+
+// The tile exponent a batch of gates is run with: 2^11 (the faster CTA shape) unless that costs a run more.
+int plan_runs(const iqsb_fgate *gates, int ngates, unsigned log2_local, bool reorder, int *order, int *run_end, uint8_t *tiles, int max_runs, int *nruns) {
+  if (ngates == 0 || log2_local <= (unsigned)kSmallTile || kTile <= kSmallTile)
+    return plan_runs_k(gates, ngates, log2_local, reorder, (unsigned)kTile, order, run_end, tiles, max_runs, nruns);
+  std::vector<int> order_s((size_t)ngates), end_s((size_t)ngates);
+  std::vector<uint8_t> tiles_s((size_t)ngates * 16);
+  int nruns_s = 0;
+  IQSB_TRY(plan_runs_k(gates, ngates, log2_local, reorder, (unsigned)kSmallTile, order_s.data(), end_s.data(), tiles_s.data(), ngates, &nruns_s));
+  IQSB_TRY(plan_runs_k(gates, ngates, log2_local, reorder, (unsigned)kTile, order, run_end, tiles, max_runs, nruns));
+  if (nruns_s <= *nruns) {
+    IQSB_REQUIRE(nruns_s <= max_runs, "iqsb_plan_fused: more than %d runs", max_runs);
+    memcpy(order, order_s.data(), sizeof(int) * (size_t)ngates);
+    memcpy(run_end, end_s.data(), sizeof(int) * (size_t)nruns_s);
+    memcpy(tiles, tiles_s.data(), (size_t)nruns_s * 16);
+    *nruns = nruns_s;
+  }
   return IQSB_OK;
 }
 

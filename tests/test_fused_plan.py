@@ -5,13 +5,20 @@ from pkg import capi
 
 H = np.array([1, 0, 1, 0, 1, 0, -1, 0.0]) / np.sqrt(2)
 X = np.array([0, 0, 1, 0, 1, 0, 0, 0.0])
-K = len(capi.plan_fused([(0, 0, 0, H)], 40)[0][2])  # tile exponent the library was built with
+K = len(capi.plan_fused([(0, 0, 0, H)], 40)[0][2])  # tile exponent of the faster CTA shape (2^11 amplitudes, 128 threads)
+KBIG = K + 1  # tiles of 2^12 amplitudes (256 threads): taken when they save a run
+
+
+def tile_sizes_ok(tiles, M):
+    sizes = {len(t) for t in tiles}
+    return len(sizes) == 1 and sizes <= {min(K, M), min(KBIG, M)}
 
 
 def check_cover(gates, runs, M):
     assert runs[0][0] == 0 and runs[-1][1] == len(gates)
+    assert tile_sizes_ok([tile for _, _, tile in runs], M)
     for (first, last, tile), nxt in zip(runs, runs[1:] + [None]):
-        assert first < last and len(tile) == min(K, M) and tile == sorted(set(tile))
+        assert first < last and tile == sorted(set(tile))
         assert tile[: min(4, M)] == list(range(min(4, M)))  # low positions always inside: 256-byte runs
         for k in range(first, last):
             assert gates[k][2] in tile  # every target of the run is in its tile
@@ -73,8 +80,9 @@ def check_order(gates, plan, M):
     order = [i for run, _ in plan for i in run]
     assert sorted(order) == list(range(len(gates)))  # every gate exactly once
     when = {i: k for k, i in enumerate(order)}
+    assert tile_sizes_ok([tile for _, tile in plan], M)
     for run, tile in plan:
-        assert tile == sorted(set(tile)) and len(tile) == min(K, M)
+        assert tile == sorted(set(tile))
         for i in run:
             assert gates[i][2] in tile
     for i in range(len(gates)):
@@ -184,7 +192,7 @@ def test_schedule_of_a_bench_layer_absorbs_the_cnots():
         assert len({t["group"] for t in first_run}) == 4
         assert sum(1 for t in first_run if t["cls"] == CLS["x"]) >= 5
         assert all(t["trail"] for t in first_run if t["cls"] == CLS["x"])  # the CNOTs cost no instruction on the data
-        assert len(groups) <= 12
+        assert len(groups) <= 14
 
 
 def test_random_schedules():
@@ -197,3 +205,17 @@ def test_random_schedules():
             gates.append((int(rng.integers(0, 2)), c, t, mats[int(rng.integers(0, len(mats)))]))
         check_trace(gates, M)
         check_trace(gates, M, reorder=False)
+
+
+def test_tile_size_is_the_small_one_unless_it_costs_a_run():
+    # 12 distinct targets: one run of 2^12-amplitude tiles, two of 2^11 -> the big tile
+    gates = [(0, 0, q, H) for q in range(12)]
+    (first, last, tile), = capi.plan_fused(gates, 32)
+    assert len(tile) == KBIG
+    # 32 targets: four runs either way -> the small tile (faster CTA shape)
+    gates = [(0, 0, q, H) for q in range(32)]
+    runs = capi.plan_fused(gates, 32)
+    assert len(runs) == 4 and all(len(t) == K for _, _, t in runs)
+    # a register smaller than the small tile is one tile
+    (first, last, tile), = capi.plan_fused([(0, 0, 3, H)], 9)
+    assert len(tile) == 9

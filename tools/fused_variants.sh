@@ -5,8 +5,9 @@ set -e
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()" >/dev/null
 variants=(
-  "r3mb3:"
-  "r4mb2:-DIQSB_FUSED_REGBITS=4 -DIQSB_FUSED_MINBLOCKS=2"
+  "t12th256mb3:"
+  "t11th128mb6:-DIQSB_FUSED_TILE=11 -DIQSB_FUSED_THREADS=128 -DIQSB_FUSED_MINBLOCKS=6"
+  "t12th128mb3:-DIQSB_FUSED_THREADS=128 -DIQSB_FUSED_MINBLOCKS=3"
 )
 for v in "${variants[@]}"; do
   name=${v%%:*}; flags=${v#*:}

@@ -202,6 +202,13 @@ typedef struct iqsb_fused_trace {
 int iqsb_plan_fused_trace(const iqsb_fgate *gates, int ngates, unsigned log2_local, int reorder, iqsb_fused_trace *out, uint8_t *group_pos,
                           int *ngroups);
 
+/* Pure host function: the raw descriptors of that schedule (tile positions, group headers with their slot
+ * tables and write-back bases, gates with class / control / matrix), as the kernel receives them; the
+ * layout is documented at the definition (csrc/kernels_fused.cu) and mirrored by tests/fused_model.py, a
+ * CPU model of the kernel used to check the schedule against the oracle without a GPU.  out == NULL:
+ * only *used (the size needed) is returned. */
+int iqsb_plan_fused_dump(const iqsb_fgate *gates, int ngates, unsigned log2_local, int reorder, void *out, size_t cap, size_t *used);
+
 /* ---- reductions (warp-shuffle + fixed-order second stage; deterministic run to run) -- */
 /* sum |a|^2 over local amplitudes with bit pos == 1: GetProbability (src/qureg_measure.cpp:150-167) */
 int iqsb_prob1(iqsb_state *st, unsigned pos, double *out);

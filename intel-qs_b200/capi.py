@@ -139,6 +139,16 @@ def plan_fused_trace(gates, log2_local, reorder=True):
     return trace, groups
 
 
+def plan_fused_dump(gates, log2_local, reorder=True):
+    """Host-only: the raw descriptor blob iqsb_fused hands to its kernel (see iqsb_plan_fused_dump)."""
+    arr = _fgates(gates)
+    used = ctypes.c_size_t()
+    _chk(load().iqsb_plan_fused_dump(arr, len(gates), log2_local, int(bool(reorder)), None, 0, ctypes.byref(used)))
+    buf = ctypes.create_string_buffer(max(used.value, 1))
+    _chk(load().iqsb_plan_fused_dump(arr, len(gates), log2_local, int(bool(reorder)), buf, used.value, ctypes.byref(used)))
+    return bytes(buf.raw[: used.value])
+
+
 def plan_permute_global_bits(rank, nranks, dst_rank_bit):
     """Host-only: (source rank, destination rank, pairwise, identity) of a rank-bit permutation for `rank`."""
     a = np.ascontiguousarray(dst_rank_bit, dtype=np.uint8)
@@ -214,6 +224,7 @@ def load():
         "iqsb_plan_fused": [c_vp, c_int, c_uint, c_vp, c_vp, c_int, ctypes.POINTER(c_int)],
         "iqsb_plan_fused_order": [c_vp, c_int, c_uint, c_int, c_vp, c_vp, c_vp, c_int, ctypes.POINTER(c_int)],
         "iqsb_plan_permute_global_bits": [c_int, c_int, c_vp, c_uint, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
+        "iqsb_plan_fused_dump": [c_vp, c_int, c_uint, c_int, c_vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],
         "iqsb_plan_fused_trace": [c_vp, c_int, c_uint, c_int, c_vp, c_vp, ctypes.POINTER(c_int)],
         "iqsb_prob1": [c_vp, c_uint, ctypes.POINTER(c_dbl)],
         "iqsb_parity_expect": [c_vp, c_u64, c_u64, ctypes.POINTER(c_dbl)],

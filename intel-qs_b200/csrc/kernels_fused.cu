@@ -933,6 +933,50 @@ extern "C" int iqsb_plan_fused_trace(const iqsb_fgate *gates, int ngates, unsign
   return IQSB_OK;
 }
 
+// Pure host function: the raw descriptors of the schedule (what the kernel is given), for tools and
+// for the CPU model of the kernel in tests/fused_model.py.  Layout of out[]: int32 nruns; per run: int32 nS,
+// uint8 pos[12], int32 nbatches, then nbatches blocks of {int32 ngroups, ngates, 0, 0; GroupDesc[24];
+// FGate<double>[48]} exactly as built for the launch.  *used = bytes written (or needed when cap is too small).
+extern "C" int iqsb_plan_fused_dump(const iqsb_fgate *gates, int ngates, unsigned log2_local, int reorder, void *out, size_t cap, size_t *used) {
+  IQSB_REQUIRE((gates || ngates == 0) && used, "iqsb_plan_fused_dump: null argument");
+  IQSB_REQUIRE(log2_local >= (unsigned)kRegBits + 1, "iqsb_plan_fused_dump: shards below 2^%d amplitudes are not tiled", kRegBits + 1);
+  for (int i = 0; i < ngates; ++i)
+    IQSB_REQUIRE((gates[i].kind == 0 || gates[i].kind == 1) && gates[i].target >= 0 && (unsigned)gates[i].target < log2_local &&
+                     (gates[i].kind == 0 || (gates[i].control >= 0 && (unsigned)gates[i].control < log2_local && gates[i].control != gates[i].target)),
+                 "iqsb_plan_fused_dump: gate %d is not a gate on local positions", i);
+  std::vector<unsigned char> buf;
+  auto put = [&](const void *p, size_t n) { buf.insert(buf.end(), (const unsigned char *)p, (const unsigned char *)p + n); };
+  int nruns = 0;
+  std::vector<int> order((size_t)(ngates > 0 ? ngates : 1)), run_end((size_t)(ngates > 0 ? ngates : 1));
+  std::vector<uint8_t> tiles((size_t)(ngates > 0 ? ngates : 1) * 16);
+  if (ngates > 0) IQSB_TRY(plan_runs(gates, ngates, log2_local, reorder != 0, order.data(), run_end.data(), tiles.data(), ngates, &nruns));
+  int32_t v = nruns;
+  put(&v, 4);
+  int first = 0;
+  for (int r = 0; r < nruns; ++r) {
+    TileDesc td;
+    td.nS = tiles[r * 16];
+    for (int j = 0; j < kTile; ++j) td.pos[j] = tiles[r * 16 + 1 + j];
+    std::vector<int> run(order.begin() + first, order.begin() + run_end[r]);
+    first = run_end[r];
+    std::vector<unsigned char> blob;
+    int nbatches = 0;
+    build_batches<double>(gates, run, td, reorder != 0, blob, nbatches);
+    v = td.nS;
+    put(&v, 4);
+    uint8_t pos12[12] = {0};
+    for (int j = 0; j < kTile && j < 12; ++j) pos12[j] = td.pos[j];
+    put(pos12, 12);
+    v = nbatches;
+    put(&v, 4);
+    put(blob.data(), blob.size());
+  }
+  *used = buf.size();
+  if (out && cap >= buf.size()) memcpy(out, buf.data(), buf.size());
+  else IQSB_REQUIRE(out == nullptr, "iqsb_plan_fused_dump: buffer of %zu bytes is too small (%zu needed)", cap, buf.size());
+  return IQSB_OK;
+}
+
 extern "C" int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates) {
   IQSB_REQUIRE(st && (gates || ngates == 0), "iqsb_fused: null argument");
   IQSB_REQUIRE(ngates >= 0 && ngates <= kMaxFusedGates, "iqsb_fused: at most %d gates per call", kMaxFusedGates);

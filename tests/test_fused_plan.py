@@ -1,5 +1,6 @@
 """CPU: how iqsb_fused cuts a batch of gates into shared-memory tile runs (iqsb_plan_fused, pure host code)."""
 import numpy as np
+import pytest
 
 from pkg import capi
 
@@ -219,3 +220,71 @@ def test_tile_size_is_the_small_one_unless_it_costs_a_run():
     # a register smaller than the small tile is one tile
     (first, last, tile), = capi.plan_fused([(0, 0, 3, H)], 9)
     assert len(tile) == 9
+
+
+# ---- the schedule executed by a CPU model of the kernel (tests/fused_model.py) == the gate-by-gate oracle ----
+def _oracle_apply(oracle, psi, gates):
+    ref = psi.copy()
+    for kind, c, t, m in gates:
+        if kind == 0:
+            oracle.gate1(ref, t, np.ascontiguousarray(m, dtype=np.float64))
+        else:
+            oracle.cgate1(ref, c, t, np.ascontiguousarray(m, dtype=np.float64))
+    return ref
+
+
+def _model_matrices():
+    f, th = 1 / np.sqrt(2), 0.7316
+    c, s_ = np.cos(th / 2), np.sin(th / 2)
+    return [G, H, T, SX, X, X, np.array([0.5, 0.5, -0.5, -0.5, 0.5, 0.5, 0.5, 0.5]),  # general, real, diag(1,d), sqrt X, X, X, sqrt Y
+            np.array([c, 0, 0, -s_, 0, -s_, c, 0.0]), np.array([c, -s_, 0, 0, 0, 0, c, s_]),  # RX, RZ
+            np.array([0, 0, 0, -1, 0, 1, 0, 0.0]), np.array([c, 0, -s_, 0, s_, 0, c, 0.0])]  # Y, RY
+
+
+@pytest.mark.parametrize("n", [4, 5, 8, 11, 12, 14])
+def test_cpu_model_of_the_kernel_reproduces_the_oracle(oracle, n):
+    """Random circuits over every matrix class, with controls in registers / on thread bits / outside the
+    tile and many X / CNOT gates (floated, folded into write-back addresses, conditional offsets): the
+    descriptors iqsb_fused builds, executed by the CPU model of the kernel, give the oracle's state bit
+    for bit -- with and without reordering."""
+    import fused_model
+    from pkg import circuits as C
+
+    rng = np.random.Generator(np.random.MT19937(900 + n))
+    mats = _model_matrices()
+    psi = C.random_state(n, seed=n)
+    for trial, (ngates, span) in enumerate(((60, min(n, 4)), (150, n), (150, min(n, 7)))):
+        gates = []
+        for i in range(ngates):
+            m = mats[int(rng.integers(0, len(mats)))]
+            t = int(rng.integers(0, span))
+            if rng.integers(0, 2):
+                gates.append((0, 0, t, m))
+            else:
+                c = int(rng.integers(0, n))
+                while c == t:
+                    c = int(rng.integers(0, n))
+                gates.append((1, c, t, m))
+        want = _oracle_apply(oracle, psi, gates)
+        for reorder in (True, False):
+            got = fused_model.run(psi, capi.plan_fused_dump(gates, n, reorder), n)
+            assert np.array_equal(got, want), (n, trial, reorder, np.max(np.abs(got - want)))
+
+
+def test_cpu_model_on_bench_layers(oracle):
+    """the layered circuit of bench.py at 16 qubits, three layers in one call and layer by layer"""
+    import bench
+    import fused_model
+    from pkg import circuits as C
+
+    n = 16
+    layers = bench.build_layers(C, n, 3)
+    psi = C.random_state(n, seed=3)
+    allg = []
+    for layer in layers:
+        allg += [((1, int(op["q0"]), int(op["q1"])) if op["kind"] == C.CX else (0, 0, int(op["q0"]))) + (bench.named_matrix(C, int(op["kind"]), op["p"]),) for op in layer]
+    want = _oracle_apply(oracle, psi, allg)
+    got = fused_model.run(psi, capi.plan_fused_dump(allg, n), n)
+    assert np.array_equal(got, want)
+    trace, _ = capi.plan_fused_trace(allg, n)
+    assert any(t["trail"] == 2 for t in trace) and any(t["trail"] == 1 for t in trace)  # both kinds of folded CNOTs occur

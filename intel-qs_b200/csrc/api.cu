@@ -186,8 +186,6 @@ extern "C" int iqsb_finalize(iqsb_ctx *ctx) {
   cudaFree(ctx->d_flags);
   cudaFreeHost(ctx->h_result);
   cudaFreeHost(ctx->h_status);
-  cudaFreeHost(ctx->stage_h);
-  cudaFree(ctx->stage_d);
   cudaFree(ctx->d_tile_counter);
   if (ctx->slots) {
     for (int i = 0; i < kMaxEventSlots; ++i)

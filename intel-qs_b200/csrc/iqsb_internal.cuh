@@ -62,10 +62,6 @@ struct iqsb_ctx {
   int *d_flags = nullptr;        // [4]
   void *comm = nullptr;          // ncclComm_t
   iqsb_peer_table *peers = nullptr;
-  // staging ring for small argument lists (fused gate descriptors): pinned host bytes mirrored at
-  // the same offsets in device memory, consumed in stream order, so no host synchronisation per use
-  unsigned char *stage_h = nullptr, *stage_d = nullptr;
-  size_t stage_off = 0;
   int arith = IQSB_ARITH_EXACT;  // iqsb_set_arith
   iqsb_prof *prof = nullptr;     // iqsb_profile
   unsigned long long *d_tile_counter = nullptr;  // tile scheduler of the fused kernel
@@ -74,7 +70,6 @@ struct iqsb_ctx {
   int *h_status = nullptr, *d_status = nullptr;
   double barrier_timeout_s = 300.;  // IQS_B200_BARRIER_TIMEOUT_S; 0 = wait for ever
 };
-constexpr size_t kStageBytes = 1u << 20;
 
 struct iqsb_state {
   iqsb_ctx *ctx = nullptr;

@@ -1,13 +1,13 @@
 #!/bin/bash
-# Build tuning variants of the fused kernel (compile-time knobs of csrc/kernels_fused.cu) as
+# Build tuning variants of the fused kernel (compile-time knobs of csrc/kernels_fused.cu: IQSB_FUSED_TILE,
+# IQSB_FUSED_REGBITS; the CTA shape is chosen at run time) as
 # build/variants/<name>/libiqs_b200.so; tools/kbench.py picks one with IQS_B200_LIB=<path>.
 set -e
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()" >/dev/null
 variants=(
-  "t12th256mb3:"
-  "t11th128mb6:-DIQSB_FUSED_TILE=11 -DIQSB_FUSED_THREADS=128 -DIQSB_FUSED_MINBLOCKS=6"
-  "t12th128mb3:-DIQSB_FUSED_THREADS=128 -DIQSB_FUSED_MINBLOCKS=3"
+  "default:"
+  "r4:-DIQSB_FUSED_REGBITS=4"
 )
 for v in "${variants[@]}"; do
   name=${v%%:*}; flags=${v#*:}

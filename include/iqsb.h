@@ -164,12 +164,13 @@ typedef struct iqsb_fgate {
 } iqsb_fgate;
 /* Apply `ngates` gates in order with as few sweeps over HBM as possible.  Targets and controls may
  * be ANY local positions: the batch is cut into runs of gates whose targets fit in one
- * shared-memory tile (2^12 amplitudes = the 4 lowest positions + 8 positions chosen per run); each
- * run costs one read and one write of the state.  Inside a run, gates on up to three tile bits are
+ * shared-memory tile (2^12 amplitudes = the 4 lowest positions + 8 positions chosen per run, or 2^11
+ * with 7 when that costs no extra run: the smaller tile runs 6 CTAs per SM); each run costs one read
+ * and one write of the state.  Inside a run, gates on up to three tile bits are
  * applied in registers per shared-memory round trip, with arithmetic specialised to the zero
  * structure of each matrix (values identical to the full evaluation for finite amplitudes). */
 int iqsb_fused(iqsb_state *st, const iqsb_fgate *gates, int ngates);
-/* tile exponent (12, or log2(local_amps) for tiny shards) */
+/* largest tile exponent (12, or log2(local_amps) for tiny shards) */
 int iqsb_fused_max_log2tile(const iqsb_state *st);
 /* Pure host function: the runs iqsb_fused would execute.  run_end[r] = one past the last gate of
  * run r; tiles[16 r] = number of tile positions, tiles[16 r + 1 ..] = the positions (ascending); tiles holds 16 bytes per run. */

@@ -1,6 +1,7 @@
 // env.cpp -- iqs::mpi::Environment over the C ABI context (replaces reference src/mpi_env.cpp, the
 // MPI bootstrap, by an NCCL bootstrap: see include/mpi_env.hpp), plus the small free functions of
 // utils.cpp / gate_spec.cpp.
+#include <fcntl.h>
 #include <sys/time.h>
 
 #include <cassert>
@@ -155,7 +156,10 @@ void Environment::Bootstrap() {
     remove(file.c_str());
     if (iqsb_unique_id(uid) != IQSB_OK) die("cannot create the NCCL unique id");
     std::string tmp = file + ".tmp";
-    FILE *fp = fopen(tmp.c_str(), "wb");
+    // created exclusively, owner-only, never through a symlink somebody else planted in the shared directory
+    remove(tmp.c_str());
+    const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL | O_NOFOLLOW, 0600);
+    FILE *fp = fd >= 0 ? fdopen(fd, "wb") : nullptr;
     long long stamp = (long long)time(nullptr);
     if (!fp || fwrite(uid, 1, sizeof(uid), fp) != sizeof(uid) || fwrite(&stamp, sizeof(stamp), 1, fp) != 1) throw std::runtime_error("cannot write " + tmp);
     fclose(fp);

@@ -698,3 +698,33 @@ def test_full_size_32_qubits_properties(gpu_ctx):
     assert abs(a.prob1(31)) < 1e-12 and abs(a.norm2() - 1.0) < 1e-12
     a.free()
     b.free()
+
+
+def test_float_register_through_the_fused_kernel(gpu_ctx, oracle):
+    """ComplexSP through iqsb_fused (same kernel template, 8-byte slots): every matrix class, folded CNOTs,
+    controls everywhere, several runs -- against the double oracle within float tolerance."""
+    n = 14
+    mats = list(_class_matrices().values())
+    rng = np.random.Generator(np.random.MT19937(77))
+    st = gpu_ctx.alloc(1 << n, dtype=capi.F32)
+    psi = C.random_state(n, seed=4)
+    st.upload(psi.astype(np.complex64))
+    ref = psi.astype(np.complex64).astype(np.complex128)
+    gates = []
+    for i in range(120):
+        m = mats[int(rng.integers(0, len(mats)))]
+        t = int(rng.integers(0, n))
+        if rng.integers(0, 2):
+            gates.append((0, 0, t, m))
+            oracle.gate1(ref, t, m)
+        else:
+            c = int(rng.integers(0, n))
+            while c == t:
+                c = int(rng.integers(0, n))
+            gates.append((1, c, t, m))
+            oracle.cgate1(ref, c, t, m)
+    st.fused(gates)
+    got = st.download().astype(np.complex128)
+    assert np.max(np.abs(got - ref)) < 2e-5
+    assert abs(st.norm2() - 1.0) < 1e-4
+    st.free()

@@ -78,9 +78,13 @@ def main():
         for _ in range(2):
             for q in top:
                 body.named1(C.H, q).named1(C.X, q).named1(C.Y, q).named1(C.Z, q)
-        runs.append(("trivial order", body, 1, 0))
-        rev = C.Program(n).permute([n - 1 - q for q in range(n)]).extend(body).permute(list(range(n)))
-        runs.append(("reversed order (2 PermuteQubits included)", rev, 1, 0))
+        def wrap(p):  # --fusion applies to this config too
+            return C.Program(n).mode(C.FUSION_ON, a.fusion).extend(p).mode(C.FUSION_OFF) if a.fusion else p
+
+        tag = " fused" if a.fusion else ""
+        runs.append(("trivial order" + tag, wrap(body), 1, 0))
+        rev = C.Program(n).permute([n - 1 - q for q in range(n)]).extend(wrap(body)).permute(list(range(n)))
+        runs.append(("reversed order (2 PermuteQubits included)" + tag, rev, 1, 0))
     for name, prog, init, base in runs:
         r = orc.run_driver(DRIVER, prog, init=init, base_index=base, want_state=False, launcher=launcher, repeat=a.repeat)
         gates = prog.count_gates() * a.repeat

@@ -11,13 +11,18 @@
 // held by whatever bit held q's old position".  The data is brought into the reference's order by the
 // one routine that knows how to do that in few passes (RestoreCanonicalPlacement: up to three
 // local<->global pairs per NVLink pass, one whole-shard move for the rank bits, one in-place tiled
-// bit permutation for the local bits) --
-//   * at once when the register lives on one GPU (its `state` pointer is host-visible and the
-//     reference's tests read it right after the call), and
-//   * lazily when it is sharded: gates keep running on physical bits, a qubit the program moved to a
-//     "local" position is swapped in by the placement layer when a gate first needs it, and the order
-//     is restored before anything reads amplitudes by index.
+// bit permutation for the local bits), before the call returns: PermuteQubits is a collective call,
+// `psi[i]` afterwards is not -- the reference's own tests read it on the owning rank only, right after
+// a permutation (unit_test/include/state_initialization_test.hpp:213-234, found by running that suite on
+// 2 GPUs), so nothing collective may be left pending.
+// IQS_B200_LAZY_PERMUTE=1 (sharded registers with the placement layer on) leaves the data where it is:
+// gates keep running on physical bits, a qubit the program moved to a "local" position is swapped in
+// when a gate first needs it, and the order is restored by the first call that reads amplitudes by
+// index -- which then has to be made by every rank.  The qubit-reordering example at 35 qubits on
+// 8 GPUs runs 1.48 s that way.
 // All of it is pure data movement: bit-exact.
+#include <cstdlib>
+
 #include "qureg_impl.hpp"
 
 namespace iqs {
@@ -47,10 +52,14 @@ void QubitRegister<Type>::Relabel(const Permutation &target) {
   *qubit_permutation = target;
 }
 
-// after a relabelling: one GPU -> the data follows now; several -> when somebody needs the order
+// after a relabelling the data follows now, unless the program opted into the lazy scheme
 template <class Type>
 void QubitRegister<Type>::SettleAfterRelabel() {
-  if (!placement_) RestoreCanonicalPlacement();
+  static const bool lazy = [] {
+    const char *e = std::getenv("IQS_B200_LAZY_PERMUTE");
+    return e != nullptr && *e != 0 && *e != '0';
+  }();
+  if (!(placement_ && lazy)) RestoreCanonicalPlacement();
 }
 
 template <class Type>

@@ -79,6 +79,16 @@ def test_reference_passes_its_own_suite_under_the_shim():
     assert len(ok) == 66 and "StateInitializationTest.DeathTest" in ok and "SingleQubitGatesTest.DeathTest" in ok
 
 
+def test_dropin_host_classes_pass_the_reference_suite_on_cpu():
+    """conversion, TinyMatrix, ChiMatrix, RandomNumberGenerator, Permutation: the reference's test headers,
+    unchanged, against intel-qs_b200's headers + libiqs.so (tests/reference_host_suite.cpp; no register, no GPU)"""
+    rc, out = run_suite(os.path.join(os.path.dirname(DROPIN_SUITE), "suite_of_tests_host"))
+    ok, skipped, failed = report(out)
+    assert rc == 0 and not failed and not skipped, out[-3000:]
+    assert len(ok) == 17 and "ChiMatrixTest.ComplexDP" in ok and "RandomNumberGeneratorTest.SkipMethod" in ok
+    assert "PermutationTest.ObtainIntemediateInverseMaps" in ok
+
+
 # ------------------------------------------------------------------ the drop-in build on the GPU
 # One case of the 74 asserts something the arithmetic does not support: ChunkingCommunicationTest.HadamardGate
 # wants <psi|psi> of H^(x)14 |0..0> within 1e-15 of 1.  Every amplitude of that state is fl(1/sqrt 2)^14 with 14

@@ -69,6 +69,10 @@ def test_phase_counts_at_benchmark_sizes():
     swp = list(range(n))
     swp[0], swp[31] = swp[31], swp[0]
     assert len(capi.plan_permute(swp)) == 1
+    # A phase holds 12 positions, 4 of them always the lowest: it can put at most 8 positions >= 4 into their
+    # final place, so ceil(moved / 8) phases are needed whatever the schedule.  The planner is within one of that.
     rng = np.random.default_rng(0)
-    for _ in range(20):
-        assert len(capi.plan_permute([int(x) for x in rng.permutation(n)])) <= 6
+    for _ in range(200):
+        perm = [int(x) for x in rng.permutation(n)]
+        moved = sum(1 for b in range(4, n) if perm[b] != b)
+        assert -(-moved // 8) <= len(capi.plan_permute(perm)) <= -(-moved // 8) + 1

@@ -277,6 +277,10 @@ void QubitRegister<Type>::RestoreCanonicalPlacement() const {
     ++exchanges_;
     exchanged_bits_ += (uint64_t)k;
   }
+  // (the exchange splits its work between the two partners along one more local bit: a register with a
+  //  single local qubit -- two amplitudes per GPU -- cannot trade it)
+  for (unsigned g = M; g < n; ++g)
+    if (place_[g] < M) throw std::runtime_error("iqs: moving a qubit across the local/global border needs at least two local qubits per rank");
   // 2. rank bits permuted among themselves: one whole-shard move (the rank permutation of
   //    PermuteGlobalQubits, reference src/qureg_permute.cpp:149-185)
   bool ranks_ok = true;

@@ -95,7 +95,7 @@ def test_dropin_host_classes_pass_the_reference_suite_on_cpu():
 # roundings = 2^-7 (1 - 1.1e-15), in the reference as here (the gate kernels are bit-exact), so the sum of the
 # 2^14 equal squares is 1 - 2.2e-15 when it is summed exactly.  The reference's serial `+=` loses the deficit of
 # each term once the partial sum is large (the term is below half a unit in the last place of the sum) and
-# lands within 1e-16 of 1; the engine's pairwise tree sum of equal terms is exact and returns 1 - 2.0e-15.
+# lands within 1e-16 of 1; the engine's blocked pairwise sum keeps the deficit and returns 1 - 2.0e-15.
 # Both are inside the 1e-12 this repo promises for scalars; the test's 1e-15 is not a property of the state.
 HADAMARD_NORM_CASE = "ChunkingCommunicationTest.HadamardGate"
 

@@ -50,3 +50,15 @@ def test_reference_arm_under_torchrun_only_rank0_prints():
     recs = json_lines(r.stdout)
     assert len(recs) == 1
     check_line(recs[0], 2, 3, 2)
+
+
+def test_own_arm_fails_loudly_without_a_gpu():
+    """no silent CPU path behind bench.py: without a CUDA device the run ends with an error and prints no line"""
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "3"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
+    assert json_lines(r.stdout) == []
